@@ -1,0 +1,171 @@
+/* mcdp_b200.h -- C ABI of libmcdp_b200.so, the B200 (sm_100a) implementation of the
+ * Monte-Carlo hot path of WonJayne/mc_dagprop.
+ *
+ * The reference has no FFI seam: its pybind11 module calls `Simulator` directly
+ * (reference src/mc_dagprop/monte_carlo/_core.cpp:545-551).  This header is the seam a
+ * maintainer would cut there; each entry point names the reference code it replaces.
+ * INTEGRATION.md shows the C++ and ctypes stubs that bind it.
+ *
+ * Conventions: plain C types, caller-owned buffers, no exceptions across the boundary.
+ * Every function that can fail returns an int status (MCDP_OK == 0); mcdp_last_error()
+ * returns the calling thread's last message.  The binding layer rethrows it as Python
+ * RuntimeError where the reference throws std::runtime_error.  There is NO CPU fallback:
+ * without a usable CUDA device every run call fails with MCDP_ERR_CUDA.
+ *
+ * Device arrays are event-major, sample-minor: row r (an event or an activity index) of
+ * sample column s lives at base[r * ld + s]; ld (elements) must be even and >= n, bases
+ * 16-byte aligned, so that one warp reads/writes 64 adjacent samples of a row as 16-byte
+ * vectors.  Host arrays of the *_host calls are sample-major ([n][E], [n][A]) exactly like
+ * the reference's per-sample SimResult vectors (_core.cpp:65-69).
+ */
+#ifndef MCDP_B200_H
+#define MCDP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCDP_ABI_VERSION 1
+
+enum {
+    MCDP_OK = 0,
+    MCDP_ERR_INVALID = 1, /* what the reference reports as std::runtime_error (and the UB it does not check) */
+    MCDP_ERR_CUDA = 2,    /* CUDA runtime / no device / out of memory */
+    MCDP_ERR_ARG = 3      /* null pointer, bad size, bad layout */
+};
+
+/* Distribution kinds, one per reference Dist struct. p* meaning in comments. */
+enum {
+    MCDP_DIST_CONSTANT = 0,    /* ConstantDist          _core.cpp:72-76    p0 = factor                       */
+    MCDP_DIST_EXPONENTIAL = 1, /* ExponentialDist       _core.cpp:78-90    p0 = lambda (mean), p1 = max_scale */
+    MCDP_DIST_GAMMA = 2,       /* GammaDist             _core.cpp:92-105   p0 = shape, p1 = scale, p2 = max_scale */
+    MCDP_DIST_EMP_ABS = 3,     /* EmpiricalAbsoluteDist _core.cpp:110-126  table: values, weights            */
+    MCDP_DIST_EMP_REL = 4      /* EmpiricalRelativeDist _core.cpp:129-141  table: factors, weights           */
+};
+
+/* DagContext (_core.cpp:52-62) flattened.  Only Event.ts.earliest is read by the engine
+ * (_core.cpp:319,333); activity_map keys are ignored (_core.cpp:214-229).  Precedence entry i
+ * targets prec_target[i] with predecessors (pred_src[k], pred_act[k]), k in
+ * [prec_off[i], prec_off[i+1]), in the caller's order (it decides ties, _core.cpp:343). */
+typedef struct {
+    int32_t n_events;
+    const double* earliest; /* [n_events] */
+    int32_t n_act_entries;
+    const int32_t* act_idx;  /* Activity.idx; activity_count() = max + 1, gaps = zero-duration links (_core.cpp:213-219) */
+    const double* act_base;  /* Activity.minimal_duration */
+    const int32_t* act_type; /* Activity.activity_type */
+    int32_t n_prec_entries;
+    const int32_t* prec_target; /* [n_prec_entries] */
+    const int64_t* prec_off;    /* [n_prec_entries + 1] */
+    const int32_t* pred_src;    /* [prec_off[n_prec_entries]] */
+    const int32_t* pred_act;
+    double max_delay;
+} mcdp_graph_desc;
+
+/* GenericDelayGenerator::dist_map_ (_core.cpp:146-159) flattened: entry t applies to
+ * activity_type dist_type[t]; a later entry for the same type replaces an earlier one.
+ * Table of entry t: tab_values/tab_weights[tab_off[t] .. tab_off[t+1]). */
+typedef struct {
+    int32_t n_dists;
+    const int32_t* dist_type;
+    const int32_t* kind;
+    const double* p0;
+    const double* p1;
+    const double* p2;
+    const int64_t* tab_off; /* [n_dists + 1] */
+    const double* tab_values;
+    const double* tab_weights;
+} mcdp_dists_desc;
+
+/* Fused per-event statistics of the delay  realized[e] - earliest[e]  (north_star "reduced
+ * mode"; no reference counterpart -- it replaces the numpy post-processing of
+ * demo/monte_carlo.py:58-63).  All outputs ACCUMULATE (+=) so chunks, launches and GPUs add up. */
+#define MCDP_MAX_THRESHOLDS 4
+typedef struct {
+    int32_t n_thresholds;                  /* 0..4: counts of delay > thresholds[i] */
+    double thresholds[MCDP_MAX_THRESHOLDS];
+    int32_t n_bins;                        /* 0 = no histogram, else 1..256 */
+    double hist_lo, hist_hi;               /* bin = clamp(floor((delay-lo)/(hi-lo)*n_bins), 0, n_bins-1) */
+} mcdp_stats_desc;
+
+typedef struct mcdp_plan mcdp_plan;
+
+/* device ordinal for mcdp_plan_create that only validates and compiles the plan on the host
+ * (introspection and error checking without a GPU); every run call on such a plan fails with
+ * MCDP_ERR_CUDA -- there is no CPU execution path. */
+#define MCDP_DEVICE_NONE (-1)
+
+/* Per-plan options (mcdp_plan_set_option). */
+enum {
+    MCDP_OPT_STREAM_KEY = 0,    /* uint32 Philox key word 0 (default 0) */
+    MCDP_OPT_WARPS_PER_GROUP = 1, /* warps that share one 64-sample group and split each topological level; 0 = auto */
+    MCDP_OPT_GROUPS_PER_CTA = 2,  /* 64-sample groups per CTA; 0 = auto */
+    MCDP_OPT_HOST_CHUNK = 3       /* samples per device chunk in the *_host calls; 0 = auto from free HBM */
+};
+
+const char* mcdp_last_error(void);
+int32_t mcdp_abi_version(void);
+int32_t mcdp_device_count(void); /* 0 when no CUDA device is usable */
+
+/* Replaces Simulator::Simulator (_core.cpp:193-307): validates (reserved type -1, max_delay >= 0,
+ * cycle -> same messages as the reference; additionally index bounds, which the reference leaves
+ * undefined), flattens the distributions, levels the DAG, builds the evaluation-ordered
+ * event/predecessor stream and uploads it to `device`. */
+int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* dists, int32_t device, mcdp_plan** out);
+void mcdp_plan_destroy(mcdp_plan* plan);
+int32_t mcdp_plan_set_option(mcdp_plan* plan, int32_t option, int64_t value);
+
+int32_t mcdp_plan_node_count(const mcdp_plan* plan);     /* Simulator::node_count      _core.cpp:309 */
+int32_t mcdp_plan_activity_count(const mcdp_plan* plan); /* Simulator::activity_count  _core.cpp:310 */
+int64_t mcdp_plan_pred_count(const mcdp_plan* plan);
+int32_t mcdp_plan_level_count(const mcdp_plan* plan);
+int32_t mcdp_plan_device(const mcdp_plan* plan);
+/* evaluation order (a topological order; event_evaluation_order_ of _core.cpp:177) and level of each position */
+int32_t mcdp_plan_get_order(const mcdp_plan* plan, int32_t* order_out, int32_t* level_out);
+/* cumulative table the device searches for activity_type (== std::discrete_distribution's _M_cp); returns length or -1 */
+int64_t mcdp_plan_get_cumulative(const mcdp_plan* plan, int32_t activity_type, double* cp_out, int64_t cap);
+
+/* ---- device-buffer entry points (asynchronous on `stream`, a cudaStream_t passed as void*) ----
+ * Seeds: d_seeds[n] (device) or, when d_seeds is NULL, the arithmetic run seed0, seed0+1, ... */
+
+/* Replaces Simulator::run_many (_core.cpp:355-361) = n x Simulator::run (_core.cpp:312-353):
+ * fused Philox sampling + max-plus sweep.  Writes durations[A][ld], realized[E][ld], cause[E][ld]. */
+int32_t mcdp_run_full_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n, double* d_realized,
+                             double* d_durations, int32_t* d_cause, int64_t ld, void* stream);
+
+/* Propagation phase only (_core.cpp:332-350) with caller-supplied durations[A][ld]:
+ * the duration-injection mode (bit-exact fp64 parity tier). */
+int32_t mcdp_run_injected_device(mcdp_plan* plan, const double* d_durations, int64_t n, double* d_realized,
+                                 int32_t* d_cause, int64_t ld, void* stream);
+
+/* Sampling + sweep + fused statistics; no [.,n] array is written except plan-owned scratch.
+ * d_sum[E], d_sumsq[E] (f64), d_late[n_thresholds][E] (u64), d_hist[E][n_bins] (u32); NULL = skip. */
+int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n,
+                                const mcdp_stats_desc* desc, double* d_sum, double* d_sumsq,
+                                unsigned long long* d_late, uint32_t* d_hist, void* stream);
+
+/* [rows][ld] event-major -> [n][rows] sample-major (and back), for callers that hold device buffers. */
+int32_t mcdp_transpose_f64_device(const double* d_in, int64_t rows, int64_t n, int64_t ld, double* d_out, void* stream);
+int32_t mcdp_transpose_i32_device(const int32_t* d_in, int64_t rows, int64_t n, int64_t ld, int32_t* d_out, void* stream);
+
+/* ---- host-buffer entry points (synchronous; chunked, copies overlapped with compute) ---- */
+
+/* run_many with host results, sample-major like n SimResult objects: realized[n][E],
+ * durations[n][A], cause[n][E]; any output may be NULL.  Host buffers may be pageable or
+ * pinned (mcdp_host_alloc). */
+int32_t mcdp_run_many_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, double* realized, double* durations,
+                           int32_t* cause);
+int32_t mcdp_run_injected_host(mcdp_plan* plan, const double* durations, int64_t n, double* realized, int32_t* cause);
+int32_t mcdp_run_reduced_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, const mcdp_stats_desc* desc,
+                              double* sum, double* sumsq, unsigned long long* late, uint32_t* hist);
+
+void* mcdp_host_alloc(size_t bytes); /* pinned host memory, NULL on failure */
+void mcdp_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCDP_B200_H */

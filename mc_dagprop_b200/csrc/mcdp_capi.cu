@@ -1,0 +1,660 @@
+// mcdp_capi.cu -- the C ABI of include/mcdp_b200.h: plan upload, kernel launches, and the
+// chunked host-buffer calls.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mcdp_b200.h"
+#include "mcdp_plan.hpp"
+#include "mcdp_sweep.cuh"
+
+using namespace mcdp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int32_t fail(int32_t code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define MCDP_CUDA(expr)                                                                             \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(MCDP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (dev < 0) return;
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// Buffers of one in-flight chunk of a *_host call.
+struct HostSlot {
+    cudaStream_t stream = nullptr;
+    DevBuf<int32_t> seeds;
+    DevBuf<double> realized, durations;  // event-major
+    DevBuf<int32_t> cause;
+    DevBuf<double> t_realized, t_durations;  // sample-major staging
+    DevBuf<int32_t> t_cause;
+    void release() {
+        seeds.release();
+        realized.release();
+        durations.release();
+        cause.release();
+        t_realized.release();
+        t_durations.release();
+        t_cause.release();
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
+
+}  // namespace
+
+struct mcdp_plan {
+    HostPlan host;
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    // device-resident stream
+    DevBuf<EventRec> d_events;
+    DevBuf<PredRec> d_preds;
+    DevBuf<int32_t> d_level_begin;
+    DevBuf<OrphanRec> d_orphans;
+    DevBuf<DistRec> d_dists;
+    DevBuf<double> d_tab;
+    DevBuf<uint32_t> d_guide;
+    // reduced-mode variant of the stream (rows = recycled scratch slots), built on first use
+    DevBuf<EventRec> d_events_red;
+    DevBuf<PredRec> d_preds_red;
+    DevBuf<double> d_scratch;
+    bool red_ready = false;
+    // options
+    uint32_t stream_key = 0;
+    int warps_per_group = 0, groups_per_cta = 0;
+    int64_t host_chunk = 0;
+    // host-call workspaces
+    HostSlot slots[2];
+    DevBuf<double> d_stat_f64;
+    DevBuf<unsigned long long> d_stat_u64;
+    DevBuf<uint32_t> d_stat_u32;
+    std::mutex mu;  // instances are not re-entrant in the reference either; serialise instead of corrupting scratch
+
+    ~mcdp_plan() {
+        DeviceGuard g(device);
+        for (auto& s : slots) s.release();
+        d_events.release();
+        d_preds.release();
+        d_level_begin.release();
+        d_orphans.release();
+        d_dists.release();
+        d_tab.release();
+        d_guide.release();
+        d_events_red.release();
+        d_preds_red.release();
+        d_scratch.release();
+        d_stat_f64.release();
+        d_stat_u64.release();
+        d_stat_u32.release();
+    }
+};
+
+namespace {
+
+template <typename T>
+int32_t upload(DevBuf<T>& buf, const std::vector<T>& v) {
+    MCDP_CUDA(buf.ensure(v.size()));
+    if (!v.empty()) MCDP_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return MCDP_OK;
+}
+
+struct LaunchShape {
+    int wpg, gpc, threads;
+    unsigned grid;
+    size_t smem;
+    bool smem_tables;
+};
+
+// How many warps split a level, how many 64-sample groups share a CTA.
+LaunchShape choose_shape(const mcdp_plan* plan, int64_t n) {
+    const HostPlan& h = plan->host;
+    LaunchShape s{};
+    const int64_t n_groups = (n + 63) / 64;
+    int wpg = plan->warps_per_group;
+    if (wpg <= 0) {
+        // enough warps to fill the machine (~16 per SM), but never more than the DAG's levels can feed
+        const int64_t want = (int64_t(plan->sm_count) * 16 + n_groups - 1) / std::max<int64_t>(n_groups, 1);
+        const int64_t avg_width = h.n_levels > 0 ? h.E / h.n_levels : 1;
+        wpg = int(std::max<int64_t>(1, std::min<int64_t>({want, 8, std::max<int64_t>(1, avg_width / 4)})));
+    }
+    wpg = std::max(1, std::min(wpg, 16));
+    int gpc = plan->groups_per_cta;
+    if (gpc <= 0) gpc = std::max(1, 4 / wpg);
+    gpc = std::max(1, std::min({gpc, 15, 16 / wpg > 0 ? 16 / wpg : 1}));
+    s.wpg = wpg;
+    s.gpc = gpc;
+    s.threads = 32 * wpg * gpc;
+    s.grid = unsigned((n_groups + gpc - 1) / gpc);
+    const size_t need = sizeof(DistRec) * h.dists.size() + sizeof(double) * h.tab_pool.size() +
+                        sizeof(uint32_t) * h.guide_pool.size();
+    // keep several CTAs per SM resident: stage only when the tables are a modest share of shared memory
+    s.smem_tables = need > 0 && need <= std::min<size_t>(plan->smem_optin, 64 * 1024);
+    s.smem = s.smem_tables ? need : 0;
+    return s;
+}
+
+template <int MODE>
+int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p, const LaunchShape& s, cudaStream_t stream) {
+    if (p.n <= 0) return MCDP_OK;
+    if (s.smem_tables) {
+        auto k = sweep_kernel<MODE, true>;
+        if (s.smem > 48 * 1024) MCDP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s.smem)));
+        k<<<s.grid, s.threads, s.smem, stream>>>(p);
+    } else {
+        sweep_kernel<MODE, false><<<s.grid, s.threads, 0, stream>>>(p);
+    }
+    MCDP_CUDA(cudaGetLastError());
+    (void)plan;
+    return MCDP_OK;
+}
+
+SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, int64_t ld) {
+    SweepParams p{};
+    const HostPlan& h = plan->host;
+    p.events = plan->d_events.p;
+    p.preds = plan->d_preds.p;
+    p.level_begin = plan->d_level_begin.p;
+    p.orphans = plan->d_orphans.p;
+    p.dists = plan->d_dists.p;
+    p.tab_pool = plan->d_tab.p;
+    p.guide_pool = plan->d_guide.p;
+    p.n = n;
+    p.ld = ld;
+    p.n_levels = h.n_levels;
+    p.n_orphans = int32_t(h.orphans.size());
+    p.n_dists = int32_t(h.dists.size());
+    p.tab_pool_len = int32_t(h.tab_pool.size());
+    p.guide_pool_len = int32_t(h.guide_pool.size());
+    p.E = h.E;
+    p.stream_key = plan->stream_key;
+    p.warps_per_group = s.wpg;
+    return p;
+}
+
+int32_t check_layout(const void* a, int64_t n, int64_t ld) {
+    if (n < 0) return fail(MCDP_ERR_ARG, "n must be non-negative");
+    if (ld < n || (ld & 1)) return fail(MCDP_ERR_ARG, "ld must be even and >= n");
+    if (reinterpret_cast<uintptr_t>(a) & 15) return fail(MCDP_ERR_ARG, "device buffers must be 16-byte aligned");
+    return MCDP_OK;
+}
+
+template <typename T>
+int32_t launch_transpose(const T* in, int64_t in_ld, int64_t rows, int64_t cols, T* out, int64_t out_ld,
+                         cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return MCDP_OK;
+    const int64_t tiles_c = (cols + 31) / 32, tiles_r = (rows + 31) / 32;
+    if (tiles_c * tiles_r > int64_t(0x7FFFFFFF)) return fail(MCDP_ERR_ARG, "transpose too large");
+    transpose_kernel<T><<<unsigned(tiles_c * tiles_r), 256, 0, stream>>>(in, in_ld, rows, cols, out, out_ld, tiles_c);
+    MCDP_CUDA(cudaGetLastError());
+    return MCDP_OK;
+}
+
+int32_t ensure_reduced_stream(mcdp_plan* plan) {
+    if (plan->red_ready) return MCDP_OK;
+    const HostPlan& h = plan->host;
+    std::vector<EventRec> ev = h.events;
+    std::vector<PredRec> pr = h.preds;
+    for (auto& e : ev) e.row = h.slot_of_event[e.event];
+    for (auto& q : pr) q.src_row = h.slot_of_event[q.src_event];
+    int32_t rc = upload(plan->d_events_red, ev);
+    if (rc) return rc;
+    rc = upload(plan->d_preds_red, pr);
+    if (rc) return rc;
+    plan->red_ready = true;
+    return MCDP_OK;
+}
+
+int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+extern "C" {
+
+const char* mcdp_last_error(void) { return g_err.c_str(); }
+int32_t mcdp_abi_version(void) { return MCDP_ABI_VERSION; }
+
+int32_t mcdp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* dists, int32_t device, mcdp_plan** out) {
+    if (!graph || !dists || !out) return fail(MCDP_ERR_ARG, "null argument");
+    *out = nullptr;
+    mcdp_plan* plan = new (std::nothrow) mcdp_plan();
+    if (!plan) return fail(MCDP_ERR_ARG, "out of host memory");
+    std::string err;
+    bool ok = false;
+    try {
+        ok = compile_plan(*graph, *dists, plan->host, err);
+    } catch (const std::exception& e) {
+        err = e.what();
+    }
+    if (!ok) {
+        delete plan;
+        return fail(MCDP_ERR_INVALID, err);
+    }
+    if (device == MCDP_DEVICE_NONE) {
+        // validation / introspection only: every run call on this plan fails (there is no CPU path)
+        plan->device = MCDP_DEVICE_NONE;
+        *out = plan;
+        return MCDP_OK;
+    }
+    // No CPU fallback: a runnable plan lives on a CUDA device or does not exist.
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev <= 0) {
+        cudaGetLastError();
+        delete plan;
+        return fail(MCDP_ERR_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(ce));
+    }
+    if (device < 0 || device >= n_dev) {
+        delete plan;
+        return fail(MCDP_ERR_ARG, "device ordinal out of range");
+    }
+    plan->device = device;
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        delete plan;
+        return fail(MCDP_ERR_CUDA, "cudaSetDevice failed");
+    }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        plan->sm_count = prop.multiProcessorCount;
+        plan->smem_optin = prop.sharedMemPerBlockOptin;
+    }
+    const HostPlan& h = plan->host;
+    int32_t rc = upload(plan->d_events, h.events);
+    if (!rc) rc = upload(plan->d_preds, h.preds);
+    if (!rc) rc = upload(plan->d_level_begin, h.level_begin);
+    if (!rc) rc = upload(plan->d_orphans, h.orphans);
+    if (!rc) rc = upload(plan->d_dists, h.dists);
+    if (!rc) rc = upload(plan->d_tab, h.tab_pool);
+    if (!rc) rc = upload(plan->d_guide, h.guide_pool);
+    if (rc) {
+        delete plan;
+        return rc;
+    }
+    *out = plan;
+    return MCDP_OK;
+}
+
+void mcdp_plan_destroy(mcdp_plan* plan) { delete plan; }
+
+int32_t mcdp_plan_set_option(mcdp_plan* plan, int32_t option, int64_t value) {
+    if (!plan) return fail(MCDP_ERR_ARG, "null plan");
+    switch (option) {
+        case MCDP_OPT_STREAM_KEY: plan->stream_key = uint32_t(value); break;
+        case MCDP_OPT_WARPS_PER_GROUP:
+            if (value < 0 || value > 16) return fail(MCDP_ERR_ARG, "warps per group must be 0..16");
+            plan->warps_per_group = int(value);
+            break;
+        case MCDP_OPT_GROUPS_PER_CTA:
+            if (value < 0 || value > 15) return fail(MCDP_ERR_ARG, "groups per CTA must be 0..15");
+            plan->groups_per_cta = int(value);
+            break;
+        case MCDP_OPT_HOST_CHUNK:
+            if (value < 0) return fail(MCDP_ERR_ARG, "host chunk must be non-negative");
+            plan->host_chunk = value;
+            break;
+        default: return fail(MCDP_ERR_ARG, "unknown option");
+    }
+    return MCDP_OK;
+}
+
+int32_t mcdp_plan_node_count(const mcdp_plan* plan) { return plan ? plan->host.E : 0; }
+int32_t mcdp_plan_activity_count(const mcdp_plan* plan) { return plan ? plan->host.A : 0; }
+int64_t mcdp_plan_pred_count(const mcdp_plan* plan) { return plan ? plan->host.P : 0; }
+int32_t mcdp_plan_level_count(const mcdp_plan* plan) { return plan ? plan->host.n_levels : 0; }
+int32_t mcdp_plan_device(const mcdp_plan* plan) { return plan ? plan->device : -1; }
+
+int32_t mcdp_plan_get_order(const mcdp_plan* plan, int32_t* order_out, int32_t* level_out) {
+    if (!plan) return fail(MCDP_ERR_ARG, "null plan");
+    const HostPlan& h = plan->host;
+    if (order_out) std::copy(h.order.begin(), h.order.end(), order_out);
+    if (level_out) std::copy(h.level_of_pos.begin(), h.level_of_pos.end(), level_out);
+    return MCDP_OK;
+}
+
+int64_t mcdp_plan_get_cumulative(const mcdp_plan* plan, int32_t activity_type, double* cp_out, int64_t cap) {
+    if (!plan) return -1;
+    const HostPlan& h = plan->host;
+    for (size_t i = 0; i < h.dists.size(); ++i) {
+        if (h.dist_types[i] != activity_type) continue;
+        const DistRec& d = h.dists[i];
+        if (d.tab_off < 0) return -1;
+        for (int64_t k = 0; k < d.tab_len && k < cap; ++k) cp_out[k] = h.tab_pool[size_t(d.tab_off) + size_t(k)];
+        return d.tab_len;
+    }
+    return -1;
+}
+
+int32_t mcdp_run_full_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n, double* d_realized,
+                             double* d_durations, int32_t* d_cause, int64_t ld, void* stream) {
+    if (!plan) return fail(MCDP_ERR_ARG, "null plan");
+    if (plan->device < 0) return fail(MCDP_ERR_CUDA, "plan was created host-only (MCDP_DEVICE_NONE): there is no CPU execution path");
+    if (((!d_realized || !d_cause) && plan->host.E > 0) || (!d_durations && plan->host.A > 0))
+        return fail(MCDP_ERR_ARG, "null output buffer");
+    int32_t rc = check_layout(d_realized, n, ld);
+    if (!rc) rc = check_layout(d_durations, n, ld);
+    if (!rc) rc = check_layout(d_cause, n, ld);
+    if (rc) return rc;
+    DeviceGuard guard(plan->device);
+    const LaunchShape s = choose_shape(plan, n);
+    SweepParams p = base_params(plan, s, n, ld);
+    p.seeds = d_seeds;
+    p.seed0 = seed0;
+    p.realized = d_realized;
+    p.durations = d_durations;
+    p.cause = d_cause;
+    return launch_sweep<kModeFull>(plan, p, s, static_cast<cudaStream_t>(stream));
+}
+
+int32_t mcdp_run_injected_device(mcdp_plan* plan, const double* d_durations, int64_t n, double* d_realized,
+                                 int32_t* d_cause, int64_t ld, void* stream) {
+    if (!plan) return fail(MCDP_ERR_ARG, "null plan");
+    if (plan->device < 0) return fail(MCDP_ERR_CUDA, "plan was created host-only (MCDP_DEVICE_NONE): there is no CPU execution path");
+    if (((!d_realized || !d_cause) && plan->host.E > 0) || (!d_durations && plan->host.A > 0))
+        return fail(MCDP_ERR_ARG, "null buffer");
+    int32_t rc = check_layout(d_realized, n, ld);
+    if (!rc) rc = check_layout(d_durations, n, ld);
+    if (!rc) rc = check_layout(d_cause, n, ld);
+    if (rc) return rc;
+    DeviceGuard guard(plan->device);
+    const LaunchShape s = choose_shape(plan, n);
+    SweepParams p = base_params(plan, s, n, ld);
+    p.realized = d_realized;
+    p.inj = d_durations;
+    p.cause = d_cause;
+    return launch_sweep<kModeInjected>(plan, p, s, static_cast<cudaStream_t>(stream));
+}
+
+int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n,
+                                const mcdp_stats_desc* desc, double* d_sum, double* d_sumsq,
+                                unsigned long long* d_late, uint32_t* d_hist, void* stream) {
+    if (!plan || !desc) return fail(MCDP_ERR_ARG, "null argument");
+    if (plan->device < 0) return fail(MCDP_ERR_CUDA, "plan was created host-only (MCDP_DEVICE_NONE): there is no CPU execution path");
+    if (n < 0) return fail(MCDP_ERR_ARG, "n must be non-negative");
+    if (desc->n_thresholds < 0 || desc->n_thresholds > MCDP_MAX_THRESHOLDS) return fail(MCDP_ERR_ARG, "n_thresholds must be 0..4");
+    if (desc->n_bins < 0 || desc->n_bins > 4096) return fail(MCDP_ERR_ARG, "n_bins must be 0..4096");
+    if (d_hist && desc->n_bins > 0 && !(desc->hist_hi > desc->hist_lo)) return fail(MCDP_ERR_ARG, "hist_hi must exceed hist_lo");
+    std::lock_guard<std::mutex> lock(plan->mu);
+    DeviceGuard guard(plan->device);
+    int32_t rc = ensure_reduced_stream(plan);
+    if (rc) return rc;
+    const HostPlan& h = plan->host;
+    // scratch rows are recycled slots; samples are processed in chunks that bound the scratch
+    const int64_t bytes_per_sample = int64_t(std::max(h.n_slots, 1)) * 8;
+    int64_t chunk = std::max<int64_t>(64, (int64_t(2) << 30) / bytes_per_sample / 64 * 64);
+    chunk = std::min<int64_t>(chunk, round_up(std::max<int64_t>(n, 1), 64));
+    MCDP_CUDA(plan->d_scratch.ensure(size_t(std::max(h.n_slots, 1)) * size_t(chunk)));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t m = std::min(chunk, n - off);
+        const LaunchShape s = choose_shape(plan, m);
+        SweepParams p = base_params(plan, s, m, chunk);
+        p.events = plan->d_events_red.p;
+        p.preds = plan->d_preds_red.p;
+        p.seeds = d_seeds ? d_seeds + off : nullptr;
+        p.seed0 = int32_t(uint32_t(seed0) + uint32_t(off));
+        p.realized = plan->d_scratch.p;
+        p.sum = d_sum;
+        p.sumsq = d_sumsq;
+        p.late = desc->n_thresholds > 0 ? d_late : nullptr;
+        p.hist = desc->n_bins > 0 ? d_hist : nullptr;
+        p.n_thresholds = desc->n_thresholds;
+        for (int i = 0; i < desc->n_thresholds; ++i) p.thresholds[i] = desc->thresholds[i];
+        p.n_bins = desc->n_bins;
+        p.hist_lo = desc->hist_lo;
+        p.hist_scale = desc->n_bins > 0 ? double(desc->n_bins) / (desc->hist_hi - desc->hist_lo) : 0.0;
+        rc = launch_sweep<kModeReduced>(plan, p, s, st);
+        if (rc) return rc;
+    }
+    return MCDP_OK;
+}
+
+int32_t mcdp_transpose_f64_device(const double* d_in, int64_t rows, int64_t n, int64_t ld, double* d_out, void* stream) {
+    return launch_transpose<double>(d_in, ld, rows, n, d_out, rows, static_cast<cudaStream_t>(stream));
+}
+int32_t mcdp_transpose_i32_device(const int32_t* d_in, int64_t rows, int64_t n, int64_t ld, int32_t* d_out, void* stream) {
+    return launch_transpose<int32_t>(d_in, ld, rows, n, d_out, rows, static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer calls
+// ---------------------------------------------------------------------------------------------
+
+static int64_t pick_host_chunk(mcdp_plan* plan, int64_t n, bool with_durations) {
+    const HostPlan& h = plan->host;
+    if (plan->host_chunk > 0) return round_up(std::min(plan->host_chunk, std::max<int64_t>(n, 1)), 64);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(8) << 30;
+    // per sample: event-major + sample-major staging copies, two slots in flight
+    const int64_t per_sample = 2 * 2 * (int64_t(h.E) * 12 + (with_durations ? int64_t(h.A) * 8 : 0)) + 64;
+    int64_t chunk = int64_t(double(free_b) * 0.5) / per_sample / 64 * 64;
+    chunk = std::max<int64_t>(64, std::min<int64_t>(chunk, 1 << 16));
+    return std::min(chunk, round_up(std::max<int64_t>(n, 1), 64));
+}
+
+int32_t mcdp_run_many_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, double* realized, double* durations,
+                           int32_t* cause) {
+    if (!plan) return fail(MCDP_ERR_ARG, "null plan");
+    if (plan->device < 0) return fail(MCDP_ERR_CUDA, "plan was created host-only (MCDP_DEVICE_NONE): there is no CPU execution path");
+    if (n < 0) return fail(MCDP_ERR_ARG, "n must be non-negative");
+    if (n > 0 && !seeds) return fail(MCDP_ERR_ARG, "null seeds");
+    if (n == 0) return MCDP_OK;
+    std::lock_guard<std::mutex> lock(plan->mu);
+    DeviceGuard guard(plan->device);
+    const HostPlan& h = plan->host;
+    const int64_t E = h.E, A = h.A;
+    const int64_t chunk = pick_host_chunk(plan, n, true);
+    int32_t rc = MCDP_OK;
+    int64_t idx = 0;
+    for (int64_t off = 0; off < n && !rc; off += chunk, ++idx) {
+        HostSlot& sl = plan->slots[idx & 1];
+        const int64_t m = std::min(chunk, n - off);
+        if (!sl.stream) MCDP_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        // a slot is reused every other chunk: its previous copies must have drained
+        MCDP_CUDA(cudaStreamSynchronize(sl.stream));
+        MCDP_CUDA(sl.seeds.ensure(size_t(chunk)));
+        MCDP_CUDA(sl.realized.ensure(size_t(E) * size_t(chunk)));
+        MCDP_CUDA(sl.durations.ensure(size_t(A) * size_t(chunk)));
+        MCDP_CUDA(sl.cause.ensure(size_t(E) * size_t(chunk)));
+        MCDP_CUDA(cudaMemcpyAsync(sl.seeds.p, seeds + off, size_t(m) * 4, cudaMemcpyHostToDevice, sl.stream));
+        const LaunchShape s = choose_shape(plan, m);
+        SweepParams p = base_params(plan, s, m, chunk);
+        p.seeds = sl.seeds.p;
+        p.realized = sl.realized.p;
+        p.durations = sl.durations.p;
+        p.cause = sl.cause.p;
+        rc = launch_sweep<kModeFull>(plan, p, s, sl.stream);
+        if (rc) break;
+        if (realized && E) {
+            MCDP_CUDA(sl.t_realized.ensure(size_t(E) * size_t(chunk)));
+            rc = launch_transpose<double>(sl.realized.p, chunk, E, m, sl.t_realized.p, E, sl.stream);
+            if (rc) break;
+            MCDP_CUDA(cudaMemcpyAsync(realized + off * E, sl.t_realized.p, size_t(m) * E * 8, cudaMemcpyDeviceToHost, sl.stream));
+        }
+        if (durations && A) {
+            MCDP_CUDA(sl.t_durations.ensure(size_t(A) * size_t(chunk)));
+            rc = launch_transpose<double>(sl.durations.p, chunk, A, m, sl.t_durations.p, A, sl.stream);
+            if (rc) break;
+            MCDP_CUDA(cudaMemcpyAsync(durations + off * A, sl.t_durations.p, size_t(m) * A * 8, cudaMemcpyDeviceToHost, sl.stream));
+        }
+        if (cause && E) {
+            MCDP_CUDA(sl.t_cause.ensure(size_t(E) * size_t(chunk)));
+            rc = launch_transpose<int32_t>(sl.cause.p, chunk, E, m, sl.t_cause.p, E, sl.stream);
+            if (rc) break;
+            MCDP_CUDA(cudaMemcpyAsync(cause + off * E, sl.t_cause.p, size_t(m) * E * 4, cudaMemcpyDeviceToHost, sl.stream));
+        }
+    }
+    for (auto& sl : plan->slots)
+        if (sl.stream) {
+            cudaError_t e = cudaStreamSynchronize(sl.stream);
+            if (e != cudaSuccess && !rc) rc = fail(MCDP_ERR_CUDA, std::string("stream sync: ") + cudaGetErrorString(e));
+        }
+    return rc;
+}
+
+int32_t mcdp_run_injected_host(mcdp_plan* plan, const double* durations, int64_t n, double* realized, int32_t* cause) {
+    if (!plan) return fail(MCDP_ERR_ARG, "null plan");
+    if (plan->device < 0) return fail(MCDP_ERR_CUDA, "plan was created host-only (MCDP_DEVICE_NONE): there is no CPU execution path");
+    if (n < 0) return fail(MCDP_ERR_ARG, "n must be non-negative");
+    if (n == 0) return MCDP_OK;
+    const HostPlan& h = plan->host;
+    if (!durations && h.A > 0) return fail(MCDP_ERR_ARG, "null durations");
+    std::lock_guard<std::mutex> lock(plan->mu);
+    DeviceGuard guard(plan->device);
+    const int64_t E = h.E, A = h.A;
+    const int64_t chunk = pick_host_chunk(plan, n, true);
+    int32_t rc = MCDP_OK;
+    int64_t idx = 0;
+    for (int64_t off = 0; off < n && !rc; off += chunk, ++idx) {
+        HostSlot& sl = plan->slots[idx & 1];
+        const int64_t m = std::min(chunk, n - off);
+        if (!sl.stream) MCDP_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        MCDP_CUDA(cudaStreamSynchronize(sl.stream));
+        MCDP_CUDA(sl.realized.ensure(size_t(E) * size_t(chunk)));
+        MCDP_CUDA(sl.durations.ensure(size_t(A) * size_t(chunk)));
+        MCDP_CUDA(sl.t_durations.ensure(size_t(A) * size_t(chunk)));
+        MCDP_CUDA(sl.cause.ensure(size_t(E) * size_t(chunk)));
+        if (A) {
+            MCDP_CUDA(cudaMemcpyAsync(sl.t_durations.p, durations + off * A, size_t(m) * A * 8, cudaMemcpyHostToDevice, sl.stream));
+            // [m][A] sample-major -> [A][chunk] event-major
+            rc = launch_transpose<double>(sl.t_durations.p, A, m, A, sl.durations.p, chunk, sl.stream);
+            if (rc) break;
+        }
+        const LaunchShape s = choose_shape(plan, m);
+        SweepParams p = base_params(plan, s, m, chunk);
+        p.realized = sl.realized.p;
+        p.inj = sl.durations.p;
+        p.cause = sl.cause.p;
+        rc = launch_sweep<kModeInjected>(plan, p, s, sl.stream);
+        if (rc) break;
+        if (realized && E) {
+            MCDP_CUDA(sl.t_realized.ensure(size_t(E) * size_t(chunk)));
+            rc = launch_transpose<double>(sl.realized.p, chunk, E, m, sl.t_realized.p, E, sl.stream);
+            if (rc) break;
+            MCDP_CUDA(cudaMemcpyAsync(realized + off * E, sl.t_realized.p, size_t(m) * E * 8, cudaMemcpyDeviceToHost, sl.stream));
+        }
+        if (cause && E) {
+            MCDP_CUDA(sl.t_cause.ensure(size_t(E) * size_t(chunk)));
+            rc = launch_transpose<int32_t>(sl.cause.p, chunk, E, m, sl.t_cause.p, E, sl.stream);
+            if (rc) break;
+            MCDP_CUDA(cudaMemcpyAsync(cause + off * E, sl.t_cause.p, size_t(m) * E * 4, cudaMemcpyDeviceToHost, sl.stream));
+        }
+    }
+    for (auto& sl : plan->slots)
+        if (sl.stream) {
+            cudaError_t e = cudaStreamSynchronize(sl.stream);
+            if (e != cudaSuccess && !rc) rc = fail(MCDP_ERR_CUDA, std::string("stream sync: ") + cudaGetErrorString(e));
+        }
+    return rc;
+}
+
+int32_t mcdp_run_reduced_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, const mcdp_stats_desc* desc,
+                              double* sum, double* sumsq, unsigned long long* late, uint32_t* hist) {
+    if (!plan || !desc) return fail(MCDP_ERR_ARG, "null argument");
+    if (plan->device < 0) return fail(MCDP_ERR_CUDA, "plan was created host-only (MCDP_DEVICE_NONE): there is no CPU execution path");
+    if (n > 0 && !seeds) return fail(MCDP_ERR_ARG, "null seeds");
+    const int64_t E = plan->host.E;
+    const int64_t nt = std::max(desc->n_thresholds, 0), nb = std::max(desc->n_bins, 0);
+    double* d_sum = nullptr;
+    double* d_sumsq = nullptr;
+    unsigned long long* d_late = nullptr;
+    uint32_t* d_hist = nullptr;
+    int32_t* d_seeds = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(plan->mu);
+        DeviceGuard guard(plan->device);
+        MCDP_CUDA(plan->d_stat_f64.ensure(size_t(2 * E)));
+        MCDP_CUDA(plan->d_stat_u64.ensure(size_t(nt * E)));
+        MCDP_CUDA(plan->d_stat_u32.ensure(size_t(nb * E)));
+        MCDP_CUDA(plan->slots[0].seeds.ensure(size_t(std::max<int64_t>(n, 1))));
+        d_sum = plan->d_stat_f64.p;
+        d_sumsq = d_sum + E;
+        d_late = plan->d_stat_u64.p;
+        d_hist = plan->d_stat_u32.p;
+        d_seeds = plan->slots[0].seeds.p;
+        MCDP_CUDA(cudaMemset(d_sum, 0, size_t(2 * E) * 8));
+        if (nt) MCDP_CUDA(cudaMemset(d_late, 0, size_t(nt * E) * 8));
+        if (nb) MCDP_CUDA(cudaMemset(d_hist, 0, size_t(nb * E) * 4));
+        if (n) MCDP_CUDA(cudaMemcpy(d_seeds, seeds, size_t(n) * 4, cudaMemcpyHostToDevice));
+    }
+    int32_t rc = mcdp_run_reduced_device(plan, d_seeds, 0, n, desc, sum ? d_sum : nullptr, sumsq ? d_sumsq : nullptr,
+                                         late ? d_late : nullptr, hist ? d_hist : nullptr, nullptr);
+    if (rc) return rc;
+    DeviceGuard guard(plan->device);
+    MCDP_CUDA(cudaDeviceSynchronize());
+    if (sum) MCDP_CUDA(cudaMemcpy(sum, d_sum, size_t(E) * 8, cudaMemcpyDeviceToHost));
+    if (sumsq) MCDP_CUDA(cudaMemcpy(sumsq, d_sumsq, size_t(E) * 8, cudaMemcpyDeviceToHost));
+    if (late && nt) MCDP_CUDA(cudaMemcpy(late, d_late, size_t(nt * E) * 8, cudaMemcpyDeviceToHost));
+    if (hist && nb) MCDP_CUDA(cudaMemcpy(hist, d_hist, size_t(nb * E) * 4, cudaMemcpyDeviceToHost));
+    return MCDP_OK;
+}
+
+void* mcdp_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, std::max<size_t>(bytes, 1), cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void mcdp_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

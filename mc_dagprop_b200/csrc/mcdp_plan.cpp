@@ -1,0 +1,362 @@
+// mcdp_plan.cpp -- host plan compiler.  What Simulator::Simulator does once per propagator
+// (reference _core.cpp:193-307), re-thought for the device: instead of a CSR indexed by event id
+// plus a separate order vector, the output is ONE evaluation-ordered stream of 32-byte event and
+// predecessor records that the kernel reads strictly sequentially, grouped into topological
+// LEVELS (longest-path layering) so that several warps can split a level between them.
+#include "mcdp_plan.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <limits>
+#include <unordered_map>
+
+namespace mcdp {
+
+namespace {
+
+bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int32_t, int32_t>& type_to_dist,
+                 std::string& err) {
+    // A later entry for an activity_type replaces the earlier one (dist_map_[t] = ..., _core.cpp:154-158).
+    std::unordered_map<int32_t, int32_t> last_entry;
+    std::vector<int32_t> type_order;
+    for (int32_t t = 0; t < d.n_dists; ++t) {
+        if (d.dist_type[t] == -1) {  // _core.cpp:196-198
+            err = "Activity type -1 is reserved for no delay";
+            return false;
+        }
+        if (!last_entry.count(d.dist_type[t])) type_order.push_back(d.dist_type[t]);
+        last_entry[d.dist_type[t]] = t;
+    }
+    for (int32_t type : type_order) {
+        const int32_t t = last_entry[type];
+        DistRec r{};
+        r.kind = d.kind[t];
+        r.tab_off = r.guide_off = -1;
+        const double p0 = d.p0[t], p1 = d.p1[t], p2 = d.p2[t];
+        switch (r.kind) {
+            case MCDP_DIST_CONSTANT:
+                r.p[0] = p0;
+                break;
+            case MCDP_DIST_EXPONENTIAL: {
+                // The reference redraws while x > max_scale (_core.cpp:85-87) and never returns for
+                // parameters that make acceptance impossible; those are rejected here instead.
+                if (!(p0 > 0.0) || !std::isfinite(p0)) {
+                    err = "add_exponential: lambda_ must be positive and finite";
+                    return false;
+                }
+                if (!(p1 >= 0.0)) {
+                    err = "add_exponential: max_scale must be non-negative";
+                    return false;
+                }
+                r.p[0] = p0;
+                r.p[1] = p1;
+                r.p[2] = std::isinf(p1) ? 1.0 : -std::expm1(-p1 / p0);  // P(x <= max_scale)
+                break;
+            }
+            case MCDP_DIST_GAMMA: {
+                if (!(p0 > 0.0) || !std::isfinite(p0) || !(p1 > 0.0) || !std::isfinite(p1)) {
+                    err = "add_gamma: shape and scale must be positive and finite";
+                    return false;
+                }
+                if (!(p2 >= 0.0)) {
+                    err = "add_gamma: max_scale must be non-negative";
+                    return false;
+                }
+                const double malpha = p0 < 1.0 ? p0 + 1.0 : p0;  // libstdc++ random.tcc:2339
+                const double a1 = malpha - 1.0 / 3.0;
+                r.p[0] = p0;
+                r.p[1] = p1;
+                r.p[2] = p2;
+                r.p[3] = a1;
+                r.p[4] = 1.0 / std::sqrt(9.0 * a1);
+                r.p[5] = 1.0 / p0;
+                r.flags = p0 < 1.0 ? 1 : 0;
+                break;
+            }
+            case MCDP_DIST_EMP_ABS:
+            case MCDP_DIST_EMP_REL: {
+                const int64_t n = d.tab_off[t + 1] - d.tab_off[t];
+                if (n <= 0) {
+                    err = "empirical distribution needs at least one value";
+                    return false;
+                }
+                if (n > (int64_t(1) << 24)) {
+                    err = "empirical distribution table too large";
+                    return false;
+                }
+                const double* vals = d.tab_values + d.tab_off[t];
+                const double* w = d.tab_weights + d.tab_off[t];
+                r.tab_len = int32_t(n);
+                r.tab_off = int32_t(out.tab_pool.size());
+                out.tab_pool.resize(out.tab_pool.size() + 2 * size_t(n));
+                double* cp = out.tab_pool.data() + r.tab_off;
+                double* v = cp + n;
+                std::copy(vals, vals + n, v);
+                if (n < 2) {
+                    // std::discrete_distribution with < 2 weights returns 0 without a draw
+                    // (libstdc++ random.tcc:2660-2664,2703-2704).
+                    cp[0] = 1.0;
+                    r.guide_log2 = 0;
+                    r.guide_off = int32_t(out.guide_pool.size());
+                    out.guide_pool.push_back(0);
+                    break;
+                }
+                // libstdc++ random.tcc:2655-2678: normalise, partial sums, last = 1 -- same
+                // operation order, so the table is bit-identical to the reference's _M_cp.
+                double sum = 0.0;
+                for (int64_t i = 0; i < n; ++i) {
+                    if (!(w[i] >= 0.0)) {
+                        err = "empirical distribution weights must be non-negative";
+                        return false;
+                    }
+                    sum += w[i];
+                }
+                if (!(sum > 0.0) || !std::isfinite(sum)) {
+                    err = "empirical distribution weights must have a positive finite sum";
+                    return false;
+                }
+                double acc = 0.0;
+                for (int64_t i = 0; i < n; ++i) {
+                    const double p = w[i] / sum;
+                    acc = (i == 0) ? p : acc + p;
+                    cp[i] = acc;
+                }
+                cp[n - 1] = 1.0;
+                // guide table: guide[j] = first i with cp[i] >= j / G, G = 2^g >= n
+                int g = 0;
+                while ((int64_t(1) << g) < n) ++g;
+                r.guide_log2 = g;
+                r.guide_off = int32_t(out.guide_pool.size());
+                const int64_t G = int64_t(1) << g;
+                int64_t i = 0;
+                for (int64_t j = 0; j < G; ++j) {
+                    const double edge = double(j) / double(G);
+                    while (cp[i] < edge) ++i;
+                    out.guide_pool.push_back(uint32_t(i));
+                }
+                break;
+            }
+            default:
+                err = "unknown distribution kind";
+                return false;
+        }
+        type_to_dist[type] = int32_t(out.dists.size());
+        out.dists.push_back(r);
+        out.dist_types.push_back(type);
+    }
+    return true;
+}
+
+}  // namespace
+
+bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& out, std::string& err) {
+    out = HostPlan{};
+    if (g.n_events < 0 || g.n_act_entries < 0 || g.n_prec_entries < 0 || d.n_dists < 0) {
+        err = "negative element count";
+        return false;
+    }
+    std::unordered_map<int32_t, int32_t> type_to_dist;
+    if (!build_dists(d, out, type_to_dist, err)) return false;
+    if (g.max_delay < 0.0) {  // _core.cpp:199-201
+        err = "max_delay must be non-negative";
+        return false;
+    }
+    if (std::isnan(g.max_delay)) {
+        err = "max_delay must not be NaN";
+        return false;
+    }
+    const int32_t E = g.n_events;
+    out.E = E;
+    out.max_delay = g.max_delay;
+
+    // activities: link_count = max idx + 1, gaps are zero-duration links without a distribution
+    // (_core.cpp:213-229)
+    int32_t max_idx = -1;
+    for (int32_t i = 0; i < g.n_act_entries; ++i) {
+        if (g.act_idx[i] < 0) {
+            err = "Activity.idx must be non-negative";
+            return false;
+        }
+        max_idx = std::max(max_idx, g.act_idx[i]);
+    }
+    const int32_t A = max_idx + 1;
+    out.A = A;
+    std::vector<double> base(size_t(A), 0.0);
+    std::vector<uint32_t> act_dist(size_t(A), kNoDist);
+    for (int32_t i = 0; i < g.n_act_entries; ++i) {
+        const int32_t a = g.act_idx[i];
+        base[a] = g.act_base[i];
+        auto it = type_to_dist.find(g.act_type[i]);
+        act_dist[a] = it == type_to_dist.end() ? kNoDist : uint32_t(it->second);
+    }
+
+    // precedence: the last entry for a target wins (preds_by_target[tgt] = entry.second, _core.cpp:240);
+    // indices are bounds-checked here -- the reference does not (undefined behaviour there).
+    std::vector<int32_t> entry_of(size_t(E), -1);
+    for (int32_t i = 0; i < g.n_prec_entries; ++i) {
+        const int32_t tgt = g.prec_target[i];
+        if (tgt < 0 || tgt >= E) {
+            err = "precedence_list: target event index out of range";
+            return false;
+        }
+        if (g.prec_off[i + 1] < g.prec_off[i]) {
+            err = "precedence_list: offsets must be non-decreasing";
+            return false;
+        }
+        for (int64_t k = g.prec_off[i]; k < g.prec_off[i + 1]; ++k) {
+            if (g.pred_src[k] < 0 || g.pred_src[k] >= E) {
+                err = "precedence_list: predecessor event index out of range";
+                return false;
+            }
+            if (g.pred_act[k] < 0 || g.pred_act[k] >= A) {
+                err = "precedence_list: activity index out of range";
+                return false;
+            }
+        }
+        entry_of[tgt] = i;
+    }
+
+    // successor CSR over the winning entries + in-degrees
+    std::vector<int64_t> succ_off(size_t(E) + 1, 0);
+    std::vector<int32_t> indeg(size_t(E), 0);
+    int64_t P = 0;
+    for (int32_t e = 0; e < E; ++e) {
+        const int32_t en = entry_of[e];
+        if (en < 0) continue;
+        const int64_t n = g.prec_off[en + 1] - g.prec_off[en];
+        if (n > std::numeric_limits<int32_t>::max()) {
+            err = "precedence_list: fan-in too large";
+            return false;
+        }
+        indeg[e] = int32_t(n);
+        P += n;
+        for (int64_t k = g.prec_off[en]; k < g.prec_off[en + 1]; ++k) succ_off[size_t(g.pred_src[k]) + 1]++;
+    }
+    if (P > int64_t(0xFFFFFFF0u)) {
+        err = "too many precedence entries";
+        return false;
+    }
+    out.P = P;
+    for (int32_t e = 0; e < E; ++e) succ_off[size_t(e) + 1] += succ_off[e];
+    std::vector<int32_t> succ(size_t(std::max<int64_t>(P, 1)));
+    {
+        std::vector<int64_t> pos(succ_off.begin(), succ_off.end() - 1);
+        for (int32_t e = 0; e < E; ++e) {
+            const int32_t en = entry_of[e];
+            if (en < 0) continue;
+            for (int64_t k = g.prec_off[en]; k < g.prec_off[en + 1]; ++k) succ[size_t(pos[g.pred_src[k]]++)] = e;
+        }
+    }
+
+    // Kahn (_core.cpp:248-264) carrying the longest-path level of every event
+    std::vector<int32_t> level(size_t(E), 0);
+    std::vector<int32_t> queue;
+    queue.reserve(size_t(E));
+    for (int32_t e = 0; e < E; ++e)
+        if (indeg[e] == 0) queue.push_back(e);
+    for (size_t qh = 0; qh < queue.size(); ++qh) {
+        const int32_t n = queue[qh];
+        for (int64_t k = succ_off[n]; k < succ_off[size_t(n) + 1]; ++k) {
+            const int32_t dst = succ[size_t(k)];
+            level[dst] = std::max(level[dst], level[n] + 1);
+            if (--indeg[dst] == 0) queue.push_back(dst);
+        }
+    }
+    if (int32_t(queue.size()) != E) {
+        err = "Invalid DAG: cycle detected in precedence list";
+        return false;
+    }
+    int32_t n_levels = 0;
+    for (int32_t e = 0; e < E; ++e) n_levels = std::max(n_levels, level[e] + 1);
+    out.n_levels = n_levels;
+
+    // evaluation order: by level, ascending event id inside a level (counting sort)
+    out.level_begin.assign(size_t(n_levels) + 1, 0);
+    for (int32_t e = 0; e < E; ++e) out.level_begin[size_t(level[e]) + 1]++;
+    for (int32_t l = 0; l < n_levels; ++l) {
+        out.max_level_width = std::max(out.max_level_width, out.level_begin[size_t(l) + 1]);
+        out.level_begin[size_t(l) + 1] += out.level_begin[l];
+    }
+    out.order.resize(size_t(E));
+    out.level_of_pos.resize(size_t(E));
+    std::vector<int32_t> pos_of_event(static_cast<size_t>(E), 0);
+    {
+        std::vector<int32_t> cursor(out.level_begin.begin(), out.level_begin.end() - (n_levels ? 1 : 0));
+        for (int32_t e = 0; e < E; ++e) {
+            const int32_t p = cursor[level[e]]++;
+            out.order[p] = e;
+            out.level_of_pos[p] = level[e];
+            pos_of_event[e] = p;
+        }
+    }
+
+    // the stream
+    out.events.resize(size_t(E));
+    out.preds.resize(size_t(P));
+    std::vector<uint32_t> act_refs(size_t(A), 0);
+    uint32_t cursor = 0;
+    for (int32_t p = 0; p < E; ++p) {
+        const int32_t e = out.order[p];
+        EventRec& ev = out.events[p];
+        ev.row = uint32_t(e);
+        ev.event = uint32_t(e);
+        ev.pred_begin = cursor;
+        ev.earliest = g.earliest[e];
+        ev.ub = g.earliest[e] + g.max_delay;  // _core.cpp:334
+        const int32_t en = entry_of[e];
+        uint32_t fan = 0;
+        if (en >= 0) {
+            for (int64_t k = g.prec_off[en]; k < g.prec_off[en + 1]; ++k, ++fan) {
+                PredRec& pr = out.preds[cursor + fan];
+                pr.src_row = uint32_t(g.pred_src[k]);
+                pr.src_event = uint32_t(g.pred_src[k]);
+                pr.act = uint32_t(g.pred_act[k]);
+                pr.base = base[pr.act];
+                pr.dist = act_dist[pr.act];
+                pr.pad0 = pr.pad1 = 0;
+                act_refs[pr.act]++;
+            }
+        }
+        ev.fan_in = fan;
+        cursor += fan;
+        out.max_fan_in = std::max<int32_t>(out.max_fan_in, int32_t(fan));
+    }
+    for (int32_t a = 0; a < A; ++a) {
+        if (act_refs[a] == 0) out.orphans.push_back(OrphanRec{uint32_t(a), act_dist[a], base[a]});
+    }
+
+    // reduced-mode scratch slots: a slot is released once the LEVEL of the value's last consumer
+    // has completed, so warps that split a level never race on a recycled row.
+    {
+        std::vector<int32_t> last_level(static_cast<size_t>(E), 0);
+        for (int32_t e = 0; e < E; ++e) last_level[e] = level[e];
+        for (int32_t e = 0; e < E; ++e) {
+            const int32_t en = entry_of[e];
+            if (en < 0) continue;
+            for (int64_t k = g.prec_off[en]; k < g.prec_off[en + 1]; ++k)
+                last_level[g.pred_src[k]] = std::max(last_level[g.pred_src[k]], level[e]);
+        }
+        std::vector<std::vector<int32_t>> release(static_cast<size_t>(n_levels));
+        for (int32_t e = 0; e < E; ++e) release[size_t(last_level[e])].push_back(e);
+        out.slot_of_event.assign(size_t(E), 0);
+        std::vector<uint32_t> free_slots;
+        uint32_t next_slot = 0;
+        for (int32_t l = 0; l < n_levels; ++l) {
+            for (int32_t p = out.level_begin[l]; p < out.level_begin[size_t(l) + 1]; ++p) {
+                uint32_t s;
+                if (!free_slots.empty()) {
+                    s = free_slots.back();
+                    free_slots.pop_back();
+                } else {
+                    s = next_slot++;
+                }
+                out.slot_of_event[out.order[p]] = s;
+            }
+            for (int32_t e : release[size_t(l)]) free_slots.push_back(out.slot_of_event[e]);
+        }
+        out.n_slots = int32_t(next_slot);
+    }
+    return true;
+}
+
+}  // namespace mcdp

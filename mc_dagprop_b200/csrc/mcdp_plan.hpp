@@ -1,0 +1,45 @@
+// mcdp_plan.hpp -- host-side plan compiler (replaces Simulator::Simulator, reference
+// src/mc_dagprop/monte_carlo/_core.cpp:193-307).  Pure C++, no CUDA.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/mcdp_b200.h"
+#include "mcdp_records.h"
+
+namespace mcdp {
+
+struct HostPlan {
+    int32_t E = 0, A = 0;
+    int64_t P = 0;
+    double max_delay = 0.0;
+    int32_t n_levels = 0;
+    int32_t max_fan_in = 0;
+    int32_t max_level_width = 0;
+
+    // evaluation-ordered stream (rows = event ids)
+    std::vector<EventRec> events;
+    std::vector<PredRec> preds;
+    std::vector<int32_t> level_begin;  // [n_levels + 1] positions into events
+    std::vector<OrphanRec> orphans;
+
+    // distributions
+    std::vector<DistRec> dists;
+    std::vector<int32_t> dist_types;   // activity_type of dists[i]
+    std::vector<double> tab_pool;
+    std::vector<uint32_t> guide_pool;
+
+    // introspection
+    std::vector<int32_t> order;        // event id at each position
+    std::vector<int32_t> level_of_pos; // level of each position
+
+    // reduced mode: realized scratch rows recycled once every consumer of a value has run
+    std::vector<uint32_t> slot_of_event;
+    int32_t n_slots = 0;
+};
+
+// Returns false and fills `err` (the reference's std::runtime_error texts where it has one).
+bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& out, std::string& err);
+
+}  // namespace mcdp

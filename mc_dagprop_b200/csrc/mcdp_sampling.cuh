@@ -1,0 +1,174 @@
+// mcdp_sampling.cuh -- device generator "mcdp-philox-v1" (DESIGN.md section 4).
+//
+// Replaces the reference's sequential Xoshiro256++ stream (_custom_rng.hpp:551-600) and the
+// libstdc++ <random> transforms behind Dist::sample (_core.cpp:72-141) by counter-based draws
+// keyed on (seed, activity index): every (seed, activity) pair owns its random bits, so the
+// result of a sample does not depend on which thread, chunk or GPU computes it and the
+// activities can be drawn in evaluation order, fused with the max-plus sweep.
+//
+//   key     = (stream_key, 'MCDP')                     -- kernel-uniform: round keys fold to constants
+//   PAIR    ctr = (seed >> 1, act, j, 'PAIR')          -- one block serves seeds {2k, 2k+1}: 64 bits each
+//   SOLO    ctr = (seed,      act, t, 'SOLO')          -- gamma attempt t: 4 x 32 bits
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "mcdp_records.h"
+
+namespace mcdp {
+
+constexpr uint32_t kKey1 = 0x4D434450u;     // 'MCDP'
+constexpr uint32_t kTagPair = 0x50414952u;  // 'PAIR'
+constexpr uint32_t kTagSolo = 0x534F4C4Fu;  // 'SOLO'
+constexpr uint32_t kGammaMaxAttempts = 65536u;
+
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+// Philox4x32-10 (Salmon et al., SC'11).  key0 is kernel-uniform, so ptxas keeps the ten round
+// keys in uniform registers; per block this is 20 IMAD.WIDE + 20 LOP3.
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t key0) {
+    uint32_t k0 = key0, k1 = kKey1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
+        const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
+        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
+        c1 = static_cast<uint32_t>(p1);
+        c3 = static_cast<uint32_t>(p0);
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+// ((X >> 12) + 0.5) * 2^-52 for X = hi:lo, in (0,1): one exact subtraction, no int->fp conversion.
+__device__ __forceinline__ double uniform52(uint32_t lo, uint32_t hi) {
+    const uint32_t khi = hi >> 12;
+    const uint32_t klo = (lo >> 12) | (hi << 20);
+    return __hiloint2double(static_cast<int>(0x3FF00000u | khi), static_cast<int>(klo)) - (1.0 - 0x1p-53);
+}
+
+// (w + 0.5) * 2^-32 in (0,1), exact.
+__device__ __forceinline__ double uniform32(uint32_t w) {
+    return __hiloint2double(0x41300000, static_cast<int>(w)) - (1048576.0 - 0x1p-33);
+}
+
+// Table access: SMEM_TABLES => pointers address shared memory (staged copy), else global (L1/L2).
+template <bool SMEM>
+__device__ __forceinline__ double tab_ld(const double* p) {
+    if constexpr (SMEM) return *p;
+    else return __ldg(p);
+}
+template <bool SMEM>
+__device__ __forceinline__ uint32_t guide_ld(const uint32_t* p) {
+    if constexpr (SMEM) return *p;
+    else return __ldg(p);
+}
+
+// Inverse-CDF lookup with std::lower_bound semantics (first cp[i] >= u; libstdc++
+// random.tcc:2709-2713) through a guide table: start at guide[top bits of u], then scan.
+template <bool SMEM>
+__device__ __forceinline__ int emp_index(const DistRec& d, const double* tab, const uint32_t* guide, uint32_t lo,
+                                         uint32_t hi, double u) {
+    // floor(u * 2^g) == (X >> 12) >> (52 - g) == hi >> (32 - g)   (g <= 24)
+    const uint32_t j = d.guide_log2 ? (hi >> (32 - d.guide_log2)) : 0u;
+    (void)lo;
+    int idx = static_cast<int>(guide_ld<SMEM>(guide + d.guide_off + j));
+    const double* cp = tab + d.tab_off;
+    while (tab_ld<SMEM>(cp + idx) < u) ++idx;  // cp[len-1] == 1.0 > u terminates the scan
+    return idx;
+}
+
+// One gamma variate (Marsaglia-Tsang, as libstdc++ random.tcc:2352-2393, normal by Box-Muller
+// from two 32-bit uniforms), truncated to max_scale by continuing the attempt sequence -- the
+// law of the reference's `do x = dist(rng); while (x > max_scale)` loop (_core.cpp:98-104).
+__device__ __forceinline__ double gamma_variate(const DistRec& d, uint32_t seed, uint32_t act, uint32_t key0) {
+    const double scale = d.p[1], mx = d.p[2], a1 = d.p[3], a2 = d.p[4];
+    double x = 0.0;
+    for (uint32_t t = 0; t < kGammaMaxAttempts; ++t) {
+        const Philox4 w = philox4x32_10(seed, act, t, kTagSolo, key0);
+        const double n = sqrt(-2.0 * log(uniform32(w.x))) * cospi(2.0 * uniform32(w.y));
+        double v = 1.0 + a2 * n;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        const double u = uniform32(w.z);
+        const double n2 = n * n;
+        if (u > 1.0 - 0.0331 * n2 * n2 && log(u) > 0.5 * n2 + a1 * (1.0 - v + log(v))) continue;
+        x = a1 * v * scale;
+        if (d.flags & 1) x *= pow(uniform32(w.w), d.p[5]);
+        if (x > mx) continue;
+        return x;
+    }
+    return x > mx ? mx : x;  // attempt cap (the reference would spin forever here)
+}
+
+// Extra delays of one activity for the two samples a thread owns.  `paired`: the seeds are
+// {2k, 2k+1}, so one PAIR block serves both.  Returns extra (the value Dist::sample returns);
+// the caller forms base + extra with separately rounded operations like the reference build.
+template <bool SMEM>
+__device__ __forceinline__ void sample_extra2(const DistRec& d, const double* tab, const uint32_t* guide, double base,
+                                              uint32_t act, uint32_t seed_a, uint32_t seed_b, bool paired,
+                                              uint32_t key0, double& ea, double& eb) {
+    const int kind = d.kind;
+    if (kind == MCDP_DIST_CONSTANT) {
+        ea = eb = __dmul_rn(base, d.p[0]);  // _core.cpp:75
+        return;
+    }
+    if (kind == MCDP_DIST_GAMMA) {
+        ea = __dmul_rn(gamma_variate(d, seed_a, act, key0), base);
+        eb = __dmul_rn(gamma_variate(d, seed_b, act, key0), base);
+        return;
+    }
+    if ((kind == MCDP_DIST_EMP_ABS || kind == MCDP_DIST_EMP_REL) && d.tab_len < 2) {
+        // < 2 weights: index 0 without consuming a draw (libstdc++ random.tcc:2703-2704)
+        const double v = tab_ld<SMEM>(tab + d.tab_off + d.tab_len);
+        ea = eb = (kind == MCDP_DIST_EMP_ABS) ? v : __dmul_rn(v, base);
+        return;
+    }
+    // one 64-bit draw per sample
+    uint32_t lo_a, hi_a, lo_b, hi_b;
+    {
+        const Philox4 r = philox4x32_10(seed_a >> 1, act, 0u, kTagPair, key0);
+        const bool odd = seed_a & 1u;
+        lo_a = odd ? r.z : r.x;
+        hi_a = odd ? r.w : r.y;
+        lo_b = r.z;
+        hi_b = r.w;
+    }
+    if (!paired) {
+        const Philox4 r = philox4x32_10(seed_b >> 1, act, 0u, kTagPair, key0);
+        const bool odd = seed_b & 1u;
+        lo_b = odd ? r.z : r.x;
+        hi_b = odd ? r.w : r.y;
+    }
+    const double ua = uniform52(lo_a, hi_a), ub = uniform52(lo_b, hi_b);
+    if (kind == MCDP_DIST_EXPONENTIAL) {
+        // inverse CDF of the exponential truncated to [0, max_scale]: the law of the
+        // reference's rejection loop (_core.cpp:83-89), without the loop.
+        const double lam = d.p[0], mx = d.p[1], F = d.p[2];
+        double xa = -lam * log1p(-ua * F);
+        double xb = -lam * log1p(-ub * F);
+        xa = xa > mx ? mx : xa;
+        xb = xb > mx ? mx : xb;
+        ea = __dmul_rn(xa, base);
+        eb = __dmul_rn(xb, base);
+        return;
+    }
+    const double* vals = tab + d.tab_off + d.tab_len;
+    const double va = tab_ld<SMEM>(vals + emp_index<SMEM>(d, tab, guide, lo_a, hi_a, ua));
+    const double vb = tab_ld<SMEM>(vals + emp_index<SMEM>(d, tab, guide, lo_b, hi_b, ub));
+    if (kind == MCDP_DIST_EMP_ABS) {  // _core.cpp:125
+        ea = va;
+        eb = vb;
+    } else {  // _core.cpp:140
+        ea = __dmul_rn(va, base);
+        eb = __dmul_rn(vb, base);
+    }
+}
+
+}  // namespace mcdp

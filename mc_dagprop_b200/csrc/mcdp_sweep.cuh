@@ -1,0 +1,249 @@
+// mcdp_sweep.cuh -- the fused sample + max-plus sweep kernel for sm_100a.
+//
+// Replaces Simulator::run (reference _core.cpp:312-353) for a block of seeds:
+//   * one warp owns 64 adjacent samples (two per lane) of the event-major / sample-minor arrays,
+//     so every predecessor read and every realized / cause / duration write is a 16-byte
+//     vector access and a 512-byte contiguous row segment per warp;
+//   * `warps_per_group` warps share the same 64 samples and split every topological level
+//     between them (round-robin over the level's events), meeting at a named barrier per level:
+//     this is how large DAGs, whose per-sample output footprint limits the resident sample
+//     count, still fill the SMs;
+//   * the delay of each precedence entry is drawn (Philox, mcdp_sampling.cuh) at the point of
+//     use and streamed out, never re-read.
+#pragma once
+#include "mcdp_sampling.cuh"
+
+namespace mcdp {
+
+enum SweepMode { kModeFull = 0, kModeInjected = 1, kModeReduced = 2 };
+
+struct SweepParams {
+    const EventRec* events;
+    const PredRec* preds;
+    const int32_t* level_begin;
+    const OrphanRec* orphans;
+    const DistRec* dists;
+    const double* tab_pool;
+    const uint32_t* guide_pool;
+    const int32_t* seeds;  // nullptr => seed0 + sample index
+    double* realized;      // [rows][ld]  (output in full/injected mode, scratch in reduced mode)
+    double* durations;     // [A][ld]     full mode: written
+    const double* inj;     // [A][ld]     injected mode: read
+    int32_t* cause;        // [E][ld]
+    double* sum;           // reduced mode accumulators
+    double* sumsq;
+    unsigned long long* late;
+    uint32_t* hist;
+    double thresholds[MCDP_MAX_THRESHOLDS];
+    double hist_lo, hist_scale;
+    int64_t n, ld;
+    int32_t n_levels, n_orphans, n_dists, tab_pool_len, guide_pool_len;
+    int32_t n_thresholds, n_bins, E;
+    int32_t seed0;
+    uint32_t stream_key;
+    int32_t warps_per_group;
+};
+
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// std::min(a, b) of the reference build: (b < a) ? b : a  -- NOT fmin (NaN / signed-zero differ).
+__device__ __forceinline__ double ref_min(double a, double b) { return (b < a) ? b : a; }
+
+template <int MODE, bool SMEM>
+__global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ SweepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const DistRec* dists = p.dists;
+    const double* tab = p.tab_pool;
+    const uint32_t* guide = p.guide_pool;
+    if constexpr (SMEM) {
+        // stage distribution records + inverse-CDF tables + guide tables once per CTA
+        DistRec* s_dists = reinterpret_cast<DistRec*>(smem_raw);
+        double* s_tab = reinterpret_cast<double*>(smem_raw + sizeof(DistRec) * p.n_dists);
+        uint32_t* s_guide = reinterpret_cast<uint32_t*>(s_tab + p.tab_pool_len);
+        const int n16 = int(sizeof(DistRec) / 16) * p.n_dists;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x)
+            reinterpret_cast<int4*>(s_dists)[i] = __ldg(reinterpret_cast<const int4*>(p.dists) + i);
+        for (int i = threadIdx.x; i < p.tab_pool_len; i += blockDim.x) s_tab[i] = __ldg(p.tab_pool + i);
+        for (int i = threadIdx.x; i < p.guide_pool_len; i += blockDim.x) s_guide[i] = __ldg(p.guide_pool + i);
+        __syncthreads();
+        dists = s_dists;
+        tab = s_tab;
+        guide = s_guide;
+    }
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int wpg = p.warps_per_group;
+    const int group_in_cta = warp / wpg;
+    const int wsub = warp - group_in_cta * wpg;
+    const int groups_per_cta = (blockDim.x >> 5) / wpg;
+    const int64_t group = int64_t(blockIdx.x) * groups_per_cta + group_in_cta;
+    if (group * 64 >= p.n) return;  // whole group (all its warps) out of range
+    const int64_t s0 = group * 64 + 2 * lane;
+    const bool valid_a = s0 < p.n;
+    const bool valid_b = s0 + 1 < p.n;
+    const int64_t ld = p.ld;
+
+    uint32_t seed_a = 0, seed_b = 1;
+    if constexpr (MODE != kModeInjected) {
+        if (p.seeds) {
+            if (valid_a) seed_a = uint32_t(__ldg(p.seeds + s0));
+            seed_b = valid_b ? uint32_t(__ldg(p.seeds + s0 + 1)) : seed_a + 1u;
+        } else {
+            seed_a = uint32_t(p.seed0) + uint32_t(s0);
+            seed_b = seed_a + 1u;
+        }
+    }
+    const bool paired = ((seed_a & 1u) == 0u) && (seed_b == seed_a + 1u);
+    const uint32_t key0 = p.stream_key;
+
+    double* __restrict__ realized = p.realized;
+
+    for (int lvl = 0; lvl < p.n_levels; ++lvl) {
+        const int lb = __ldg(p.level_begin + lvl), le = __ldg(p.level_begin + lvl + 1);
+        for (int i = lb + wsub; i < le; i += wpg) {
+            const int4 e0 = __ldg(reinterpret_cast<const int4*>(p.events + i));
+            const double2 e1 = __ldg(reinterpret_cast<const double2*>(p.events + i) + 1);
+            const uint32_t row = uint32_t(e0.x), pred_begin = uint32_t(e0.z), fan_in = uint32_t(e0.w);
+            const double earliest = e1.x, ub = e1.y;
+            // _core.cpp:336-337
+            double lat_a = earliest, lat_b = earliest;
+            int cause_a = -1, cause_b = -1;
+            for (uint32_t k = 0; k < fan_in; ++k) {
+                const PredRec* pr = p.preds + pred_begin + k;
+                const int4 q0 = __ldg(reinterpret_cast<const int4*>(pr));
+                const int4 q1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
+                const uint32_t src_row = uint32_t(q0.x), act = uint32_t(q0.y);
+                const double base = __hiloint2double(q0.w, q0.z);
+                const uint32_t dist = uint32_t(q1.x);
+                const int src_event = q1.y;
+                double2 rs = make_double2(0.0, 0.0);
+                if (valid_a) rs = *reinterpret_cast<const double2*>(realized + size_t(src_row) * ld + s0);
+                double da, db;
+                if constexpr (MODE == kModeInjected) {
+                    double2 dd = make_double2(0.0, 0.0);
+                    if (valid_a) dd = __ldcs(reinterpret_cast<const double2*>(p.inj + size_t(act) * ld + s0));
+                    da = dd.x;
+                    db = dd.y;
+                } else {
+                    if (dist == kNoDist) {
+                        da = db = base;  // _core.cpp:304-305,325
+                    } else {
+                        double ea, eb;
+                        sample_extra2<SMEM>(dists[dist], tab, guide, base, act, seed_a, seed_b, paired, key0, ea, eb);
+                        da = __dadd_rn(base, ea);  // _core.cpp:328
+                        db = __dadd_rn(base, eb);
+                    }
+                    if constexpr (MODE == kModeFull) {
+                        if (valid_a)
+                            __stcs(reinterpret_cast<double2*>(p.durations + size_t(act) * ld + s0), make_double2(da, db));
+                    }
+                }
+                // _core.cpp:341-346
+                const double ta = ref_min(__dadd_rn(rs.x, da), ub);
+                const double tb = ref_min(__dadd_rn(rs.y, db), ub);
+                if (ta >= lat_a) {
+                    lat_a = ta;
+                    cause_a = src_event;
+                }
+                if (tb >= lat_b) {
+                    lat_b = tb;
+                    cause_b = src_event;
+                }
+            }
+            // _core.cpp:348-349
+            const double ra = ref_min(lat_a, ub), rb = ref_min(lat_b, ub);
+            if (valid_a) {
+                *reinterpret_cast<double2*>(realized + size_t(row) * ld + s0) = make_double2(ra, rb);
+                if constexpr (MODE != kModeReduced)
+                    __stcs(reinterpret_cast<int2*>(p.cause + size_t(row) * ld + s0), make_int2(cause_a, cause_b));
+            }
+            if constexpr (MODE == kModeReduced) {
+                const uint32_t ev = uint32_t(e0.y);
+                const double xa = valid_a ? ra - earliest : 0.0;
+                const double xb = valid_b ? rb - earliest : 0.0;
+                if (p.sum) {
+                    const double s = warp_sum(xa + xb);
+                    if (lane == 0) atomicAdd(p.sum + ev, s);
+                }
+                if (p.sumsq) {
+                    const double s = warp_sum(xa * xa + xb * xb);
+                    if (lane == 0) atomicAdd(p.sumsq + ev, s);
+                }
+                if (p.late) {
+                    for (int t = 0; t < p.n_thresholds; ++t) {
+                        const unsigned ma = __ballot_sync(0xFFFFFFFFu, valid_a && xa > p.thresholds[t]);
+                        const unsigned mb = __ballot_sync(0xFFFFFFFFu, valid_b && xb > p.thresholds[t]);
+                        const int c = __popc(ma) + __popc(mb);
+                        if (lane == 0 && c) atomicAdd(p.late + size_t(t) * p.E + ev, (unsigned long long)c);
+                    }
+                }
+                if (p.hist) {
+                    const int nb = p.n_bins;
+                    int ba = int(floor((xa - p.hist_lo) * p.hist_scale));
+                    int bb = int(floor((xb - p.hist_lo) * p.hist_scale));
+                    ba = min(max(ba, 0), nb - 1);
+                    bb = min(max(bb, 0), nb - 1);
+                    if (!valid_a) ba = -1 - lane;  // unique keys: match groups of size 1, skipped below
+                    if (!valid_b) bb = -1 - lane;
+                    uint32_t* h = p.hist + size_t(ev) * nb;
+                    const unsigned ga = __match_any_sync(0xFFFFFFFFu, ba);
+                    if (ba >= 0 && lane == __ffs(ga) - 1) atomicAdd(h + ba, uint32_t(__popc(ga)));
+                    const unsigned gb = __match_any_sync(0xFFFFFFFFu, bb);
+                    if (bb >= 0 && lane == __ffs(gb) - 1) atomicAdd(h + bb, uint32_t(__popc(gb)));
+                }
+            }
+        }
+        if (wpg > 1) group_barrier(1 + group_in_cta, wpg * 32);
+    }
+
+    if constexpr (MODE == kModeFull) {
+        // activities no precedence entry references still get their sampled duration (_core.cpp:323-329)
+        for (int i = wsub; i < p.n_orphans; i += wpg) {
+            const int4 o = __ldg(reinterpret_cast<const int4*>(p.orphans + i));
+            const uint32_t act = uint32_t(o.x), dist = uint32_t(o.y);
+            const double base = __hiloint2double(o.w, o.z);
+            double da = base, db = base;
+            if (dist != kNoDist) {
+                double ea, eb;
+                sample_extra2<SMEM>(dists[dist], tab, guide, base, act, seed_a, seed_b, paired, key0, ea, eb);
+                da = __dadd_rn(base, ea);
+                db = __dadd_rn(base, eb);
+            }
+            if (valid_a) __stcs(reinterpret_cast<double2*>(p.durations + size_t(act) * ld + s0), make_double2(da, db));
+        }
+    }
+}
+
+// out[c][r] = in[r][c]  (in: rows x cols with row stride in_ld; out: cols x rows, stride out_ld).
+// 1-D grid of 32x32 tiles (either extent can exceed the 65535 limit of grid.y).
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ in, int64_t in_ld, int64_t rows,
+                                                        int64_t cols, T* __restrict__ out, int64_t out_ld,
+                                                        int64_t tiles_c) {
+    __shared__ T tile[32][33];
+    const int64_t tile_r = int64_t(blockIdx.x) / tiles_c, tile_c = int64_t(blockIdx.x) - tile_r * tiles_c;
+    const int64_t c0 = tile_c * 32, r0 = tile_r * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int64_t r = r0 + ty + j, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + j][tx] = in[r * in_ld + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+        const int64_t c = c0 + ty + j, r = r0 + tx;
+        if (r < rows && c < cols) out[c * out_ld + r] = tile[tx][ty + j];
+    }
+}
+
+}  // namespace mcdp
