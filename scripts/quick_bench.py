@@ -1,0 +1,44 @@
+"""Scratch timing of the fused kernel (device buffers, CUDA events). Not the contract bench."""
+import sys, time, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from mc_dagprop_b200 import capi, synth
+
+def run(name, dag, dists, n, wpg=0, gpc=0, reps=3):
+    plan = capi.Plan(dag, dists, device=0)
+    if wpg: plan.set_option(capi.OPT_WARPS_PER_GROUP, wpg)
+    if gpc: plan.set_option(capi.OPT_GROUPS_PER_CTA, gpc)
+    E, A = plan.E, plan.A
+    ld = n
+    dev = torch.device("cuda:0")
+    realized = torch.empty((E, ld), dtype=torch.float64, device=dev)
+    dur = torch.empty((A, ld), dtype=torch.float64, device=dev)
+    cause = torch.empty((E, ld), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    ts = []
+    for i in range(reps + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        plan.run_full_device(n, realized, dur, cause, ld, seed0=i * n, stream=st)
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    t = min(ts[1:]) * 1e-3
+    es = n * A / t
+    bpe = 16 + 12 * E / A
+    print(f"{name}: E={E} A={A} n={n} wpg={wpg} gpc={gpc} {t*1e3:.2f} ms  {es:.3e} edge-samples/s  "
+          f"{es*bpe/1e9:.0f} GB/s algorithmic ({es*bpe/6546.9e9*100:.1f}% of 6546.9)", flush=True)
+    del realized, dur, cause
+    plan.close()
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "c2"
+    if which == "c2":
+        dag, d = synth.c2_layered()
+        for n in (65536, 262144):
+            for wpg, gpc in ((1, 4), (1, 8), (2, 2), (4, 1), (4, 2)):
+                run("c2", dag, d, n, wpg, gpc)
+    elif which == "c3":
+        dag, d = synth.c3_network()
+        for n in (16384, 32768):
+            for wpg, gpc in ((2, 2), (4, 1), (4, 2), (8, 1), (8, 2), (16, 1)):
+                run("c3", dag, d, n, wpg, gpc)
