@@ -1,0 +1,498 @@
+// pybind_core.cpp -- Python module `mc_dagprop_b200.monte_carlo._core` (re-exported as
+// `mc_dagprop.monte_carlo._core` by the alias package): the reference's Python surface
+// (reference src/mc_dagprop/monte_carlo/_core.cpp:366-552, typed by _core.pyi) on top of the
+// C ABI of include/mcdp_b200.h.  Same class names, constructor/keyword names, frozen-dataclass
+// treatment, numpy-view result properties and RuntimeError behaviour; the engine underneath is
+// the sm_100a library.  The data-model structs live in a namespace so the module can coexist in
+// one process with the reference's own _core (whose types are global-namespace).
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstdint>
+#include <limits>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "mcdp_b200.h"
+
+namespace py = pybind11;
+
+namespace mcdp_py {
+
+using EventIndex = int;
+using ActivityIndex = int;
+using ActivityType = int;
+using Preds = std::vector<std::pair<EventIndex, ActivityIndex>>;
+
+struct PairHash {
+    size_t operator()(const std::pair<int, int>& p) const noexcept {
+        return std::hash<int>{}(p.first) ^ (std::hash<int>{}(p.second) << 1);
+    }
+};
+
+// ---- data model (reference _core.cpp:36-62) ----
+struct EventTimestamp {
+    double earliest, latest, actual;
+};
+struct Event {
+    std::string event_id;
+    EventTimestamp ts;
+};
+struct Activity {
+    ActivityIndex idx;
+    double duration;
+    ActivityType activity_type;
+};
+struct DagContext {
+    std::vector<Event> events;
+    std::unordered_map<std::pair<EventIndex, EventIndex>, Activity, PairHash> activity_map;
+    std::vector<std::pair<EventIndex, Preds>> precedence_list;
+    double max_delay;
+    DagContext(std::vector<Event> ev, std::unordered_map<std::pair<EventIndex, EventIndex>, Activity, PairHash> am,
+               std::vector<std::pair<EventIndex, Preds>> pl, double md)
+        : events(std::move(ev)), activity_map(std::move(am)), precedence_list(std::move(pl)), max_delay(md) {}
+};
+
+// ---- results: one shared batch, per-sample views (reference SimResult, _core.cpp:65-69) ----
+struct SimBatch {
+    size_t n = 0, E = 0, A = 0;
+    std::vector<double> realized, durations;
+    std::vector<int32_t> cause;
+};
+struct SimResult {
+    std::shared_ptr<SimBatch> batch;
+    size_t row = 0;
+    double* realized() const { return batch->realized.data() + row * batch->E; }
+    double* durations() const { return batch->durations.data() + row * batch->A; }
+    int32_t* cause() const { return batch->cause.data() + row * batch->E; }
+};
+
+// ---- generator: parameter tables only; sampling happens on the device ----
+struct DistSpec {
+    int kind = 0;
+    double p0 = 0, p1 = 0, p2 = 0;
+    std::vector<double> values, weights;
+};
+class GenericDelayGenerator {
+   public:
+    std::map<ActivityType, DistSpec> dist_map_;
+    int seed_ = 0;
+    // reference _core.cpp:153: seeds an RNG the simulator never reads -- kept, and equally unobservable
+    void set_seed(int s) { seed_ = s; }
+    void add_constant(ActivityType t, double f) { dist_map_[t] = DistSpec{MCDP_DIST_CONSTANT, f, 0, 0, {}, {}}; }
+    void add_exponential(ActivityType t, double lam, double mx) {
+        dist_map_[t] = DistSpec{MCDP_DIST_EXPONENTIAL, lam, mx, 0, {}, {}};
+    }
+    void add_gamma(ActivityType t, double k, double s, double m) { dist_map_[t] = DistSpec{MCDP_DIST_GAMMA, k, s, m, {}, {}}; }
+    void add_table(int kind, ActivityType t, std::vector<double> v, std::vector<double> w) {
+        if (v.size() != w.size())  // reference _core.cpp:119-120,134-135
+            throw std::runtime_error(kind == MCDP_DIST_EMP_ABS
+                                         ? "EmpiricalAbsoluteDist: values and weights must have same length"
+                                         : "EmpiricalRelativeDist: factors and weights must have same length");
+        dist_map_[t] = DistSpec{kind, 0, 0, 0, std::move(v), std::move(w)};
+    }
+};
+
+[[noreturn]] void throw_last() { throw std::runtime_error(mcdp_last_error()); }
+
+struct FlatDists {
+    std::vector<int32_t> type, kind;
+    std::vector<double> p0, p1, p2, values, weights;
+    std::vector<int64_t> off{0};
+    mcdp_dists_desc desc{};
+    explicit FlatDists(const GenericDelayGenerator& g) {
+        for (const auto& kv : g.dist_map_) {
+            type.push_back(kv.first);
+            kind.push_back(kv.second.kind);
+            p0.push_back(kv.second.p0);
+            p1.push_back(kv.second.p1);
+            p2.push_back(kv.second.p2);
+            values.insert(values.end(), kv.second.values.begin(), kv.second.values.end());
+            weights.insert(weights.end(), kv.second.weights.begin(), kv.second.weights.end());
+            off.push_back(int64_t(values.size()));
+        }
+        desc.n_dists = int32_t(type.size());
+        desc.dist_type = type.data();
+        desc.kind = kind.data();
+        desc.p0 = p0.data();
+        desc.p1 = p1.data();
+        desc.p2 = p2.data();
+        desc.tab_off = off.data();
+        desc.tab_values = values.data();
+        desc.tab_weights = weights.data();
+    }
+};
+
+template <typename T>
+const T* arr_ptr(const py::array_t<T, py::array::c_style | py::array::forcecast>& a) {
+    return a.data();
+}
+
+// ---- the propagator (reference Simulator, _core.cpp:162-362) ----
+class MonteCarloPropagator {
+    mcdp_plan* plan_ = nullptr;
+
+   public:
+    MonteCarloPropagator(const DagContext& ctx, const GenericDelayGenerator& gen, int device) {
+        // flatten the Python-side containers (the by-value conversion the reference also pays, _core.cpp:425-428)
+        std::vector<double> earliest;
+        earliest.reserve(ctx.events.size());
+        for (const auto& e : ctx.events) earliest.push_back(e.ts.earliest);
+        std::vector<int32_t> a_idx, a_type;
+        std::vector<double> a_base;
+        a_idx.reserve(ctx.activity_map.size());
+        for (const auto& kv : ctx.activity_map) {
+            a_idx.push_back(kv.second.idx);
+            a_base.push_back(kv.second.duration);
+            a_type.push_back(kv.second.activity_type);
+        }
+        std::vector<int32_t> tgt, src, act;
+        std::vector<int64_t> off{0};
+        for (const auto& entry : ctx.precedence_list) {
+            tgt.push_back(entry.first);
+            for (const auto& pr : entry.second) {
+                src.push_back(pr.first);
+                act.push_back(pr.second);
+            }
+            off.push_back(int64_t(src.size()));
+        }
+        mcdp_graph_desc g{};
+        g.n_events = int32_t(earliest.size());
+        g.earliest = earliest.data();
+        g.n_act_entries = int32_t(a_idx.size());
+        g.act_idx = a_idx.data();
+        g.act_base = a_base.data();
+        g.act_type = a_type.data();
+        g.n_prec_entries = int32_t(tgt.size());
+        g.prec_target = tgt.data();
+        g.prec_off = off.data();
+        g.pred_src = src.data();
+        g.pred_act = act.data();
+        g.max_delay = ctx.max_delay;
+        create(g, gen, device);
+    }
+
+    // additive: array ingest without per-object conversion
+    MonteCarloPropagator(py::array_t<double, py::array::c_style | py::array::forcecast> earliest,
+                         py::array_t<int32_t, py::array::c_style | py::array::forcecast> act_idx,
+                         py::array_t<double, py::array::c_style | py::array::forcecast> act_base,
+                         py::array_t<int32_t, py::array::c_style | py::array::forcecast> act_type,
+                         py::array_t<int32_t, py::array::c_style | py::array::forcecast> prec_target,
+                         py::array_t<int64_t, py::array::c_style | py::array::forcecast> prec_off,
+                         py::array_t<int32_t, py::array::c_style | py::array::forcecast> pred_src,
+                         py::array_t<int32_t, py::array::c_style | py::array::forcecast> pred_act, double max_delay,
+                         const GenericDelayGenerator& gen, int device) {
+        if (act_idx.size() != act_base.size() || act_idx.size() != act_type.size())
+            throw std::runtime_error("from_arrays: activity arrays must have the same length");
+        if (pred_src.size() != pred_act.size()) throw std::runtime_error("from_arrays: pred_src and pred_act differ in length");
+        if (prec_off.size() != prec_target.size() + 1) throw std::runtime_error("from_arrays: prec_off must have len(prec_target)+1 entries");
+        if (prec_off.size() && (prec_off.data()[0] != 0 || prec_off.data()[prec_off.size() - 1] != pred_src.size()))
+            throw std::runtime_error("from_arrays: prec_off must start at 0 and end at len(pred_src)");
+        mcdp_graph_desc g{};
+        g.n_events = int32_t(earliest.size());
+        g.earliest = earliest.data();
+        g.n_act_entries = int32_t(act_idx.size());
+        g.act_idx = act_idx.data();
+        g.act_base = act_base.data();
+        g.act_type = act_type.data();
+        g.n_prec_entries = int32_t(prec_target.size());
+        g.prec_target = prec_target.data();
+        g.prec_off = prec_off.data();
+        g.pred_src = pred_src.data();
+        g.pred_act = pred_act.data();
+        g.max_delay = max_delay;
+        create(g, gen, device);
+    }
+
+    void create(const mcdp_graph_desc& g, const GenericDelayGenerator& gen, int device) {
+        FlatDists fd(gen);
+        int32_t rc;
+        {
+            py::gil_scoped_release release;
+            rc = mcdp_plan_create(&g, &fd.desc, device, &plan_);
+        }
+        if (rc != MCDP_OK) throw_last();
+    }
+
+    ~MonteCarloPropagator() { mcdp_plan_destroy(plan_); }
+    MonteCarloPropagator(const MonteCarloPropagator&) = delete;
+    MonteCarloPropagator& operator=(const MonteCarloPropagator&) = delete;
+
+    int node_count() const { return mcdp_plan_node_count(plan_); }
+    int activity_count() const { return mcdp_plan_activity_count(plan_); }
+    int level_count() const { return mcdp_plan_level_count(plan_); }
+    int device() const { return mcdp_plan_device(plan_); }
+    void set_option(int option, int64_t value) {
+        if (mcdp_plan_set_option(plan_, option, value) != MCDP_OK) throw_last();
+    }
+
+    std::shared_ptr<SimBatch> run_batch(const std::vector<int>& seeds) {
+        auto b = std::make_shared<SimBatch>();
+        b->n = seeds.size();
+        b->E = size_t(node_count());
+        b->A = size_t(activity_count());
+        b->realized.resize(b->n * b->E);
+        b->durations.resize(b->n * b->A);
+        b->cause.resize(b->n * b->E);
+        static_assert(sizeof(int) == sizeof(int32_t), "seeds are C ints");
+        int32_t rc = mcdp_run_many_host(plan_, reinterpret_cast<const int32_t*>(seeds.data()), int64_t(b->n),
+                                        b->realized.data(), b->durations.data(), b->cause.data());
+        if (rc != MCDP_OK) throw_last();
+        return b;
+    }
+
+    SimResult run(int seed) {  // reference _core.cpp:312-353
+        std::shared_ptr<SimBatch> b;
+        {
+            py::gil_scoped_release release;
+            b = run_batch(std::vector<int>{seed});
+        }
+        return SimResult{b, 0};
+    }
+
+    std::vector<SimResult> run_many(const std::vector<int>& seeds) {  // reference _core.cpp:355-361
+        std::shared_ptr<SimBatch> b;
+        {
+            py::gil_scoped_release release;
+            b = run_batch(seeds);
+        }
+        std::vector<SimResult> out;
+        out.reserve(seeds.size());
+        for (size_t i = 0; i < seeds.size(); ++i) out.push_back(SimResult{b, i});
+        return out;
+    }
+
+    // additive: one [n,E] / [n,A] / [n,E] array triple instead of n SimResult objects
+    py::tuple run_many_arrays(py::array_t<int32_t, py::array::c_style | py::array::forcecast> seeds) {
+        const int64_t n = seeds.size(), E = node_count(), A = activity_count();
+        py::array_t<double> r({n, E}), d({n, A});
+        py::array_t<int32_t> c({n, E});
+        int32_t rc;
+        {
+            py::gil_scoped_release release;
+            rc = mcdp_run_many_host(plan_, seeds.data(), n, r.mutable_data(), d.mutable_data(), c.mutable_data());
+        }
+        if (rc != MCDP_OK) throw_last();
+        return py::make_tuple(r, d, c);
+    }
+
+    // additive: duration injection (propagation phase only, _core.cpp:332-350)
+    py::tuple run_with_durations(py::array_t<double, py::array::c_style | py::array::forcecast> durations) {
+        const int64_t E = node_count(), A = activity_count();
+        if (durations.ndim() != 2 || durations.shape(1) != A)
+            throw std::runtime_error("run_with_durations: durations must have shape [n, activity_count()]");
+        const int64_t n = durations.shape(0);
+        py::array_t<double> r({n, E});
+        py::array_t<int32_t> c({n, E});
+        int32_t rc;
+        {
+            py::gil_scoped_release release;
+            rc = mcdp_run_injected_host(plan_, durations.data(), n, r.mutable_data(), c.mutable_data());
+        }
+        if (rc != MCDP_OK) throw_last();
+        return py::make_tuple(r, c);
+    }
+
+    // additive: fused per-event statistics of realized - earliest
+    py::dict run_many_reduced(py::array_t<int32_t, py::array::c_style | py::array::forcecast> seeds,
+                              std::vector<double> thresholds, int n_bins, double hist_lo, double hist_hi) {
+        const int64_t n = seeds.size(), E = node_count();
+        if (thresholds.size() > MCDP_MAX_THRESHOLDS) throw std::runtime_error("at most 4 thresholds");
+        mcdp_stats_desc desc{};
+        desc.n_thresholds = int32_t(thresholds.size());
+        for (size_t i = 0; i < thresholds.size(); ++i) desc.thresholds[i] = thresholds[i];
+        desc.n_bins = n_bins;
+        desc.hist_lo = hist_lo;
+        desc.hist_hi = hist_hi;
+        py::array_t<double> sum(E), sumsq(E);
+        py::array_t<unsigned long long> late({int64_t(thresholds.size()), E});
+        py::array_t<uint32_t> hist({E, int64_t(n_bins)});
+        int32_t rc;
+        {
+            py::gil_scoped_release release;
+            rc = mcdp_run_reduced_host(plan_, seeds.data(), n, &desc, sum.mutable_data(), sumsq.mutable_data(),
+                                       late.size() ? late.mutable_data() : nullptr,
+                                       hist.size() ? hist.mutable_data() : nullptr);
+        }
+        if (rc != MCDP_OK) throw_last();
+        py::dict out;
+        out["n"] = n;
+        out["sum"] = sum;
+        out["sumsq"] = sumsq;
+        out["late"] = late;
+        out["hist"] = hist;
+        return out;
+    }
+};
+
+}  // namespace mcdp_py
+
+using namespace mcdp_py;
+
+PYBIND11_MODULE(_core, m) {
+    m.doc() = "Core Monte-Carlo DAG-propagation simulator (B200 / sm_100a engine)";
+
+    py::class_<EventTimestamp> ts_cls(m, "EventTimestamp");
+    ts_cls
+        .def(py::init<double, double, double>(), py::arg("earliest"), py::arg("latest"), py::arg("actual"),
+             "Create an event timestamp (earliest, latest, actual).")
+        .def_readwrite("earliest", &EventTimestamp::earliest, "Earliest bound")
+        .def_readwrite("latest", &EventTimestamp::latest, "Latest bound")
+        .def_readwrite("actual", &EventTimestamp::actual, "Scheduled time")
+        .def("__repr__", [](const EventTimestamp& ts) {
+            return py::str("EventTimestamp(earliest={}, latest={}, actual={})").format(ts.earliest, ts.latest, ts.actual);
+        });
+
+    py::class_<Event> event_cls(m, "Event");
+    event_cls
+        .def(py::init<std::string, EventTimestamp>(), py::arg("event_id"), py::arg("timestamp"),
+             "An event node with its ID and timestamp")
+        .def_readwrite("event_id", &Event::event_id, "Node identifier")
+        .def_readwrite("timestamp", &Event::ts, "Event timing info")
+        .def("__repr__", [](const Event& ev) {
+            return py::str("Event(event_id={}, timestamp={})").format(py::repr(py::cast(ev.event_id)), py::repr(py::cast(ev.ts)));
+        });
+
+    py::class_<Activity> activity_cls(m, "Activity");
+    activity_cls
+        .def(py::init<ActivityIndex, double, ActivityType>(), py::arg("idx"), py::arg("minimal_duration"),
+             py::arg("activity_type"), "An activity (edge) with index, base duration and type")
+        .def_readwrite("idx", &Activity::idx, "Index of the activity")
+        .def_readwrite("minimal_duration", &Activity::duration, "Base duration")
+        .def_readwrite("activity_type", &Activity::activity_type, "Type ID for delay dist.")
+        .def("__repr__", [](const Activity& a) {
+            return py::str("Activity(idx={}, minimal_duration={}, activity_type={})").format(a.idx, a.duration, a.activity_type);
+        });
+
+    py::class_<DagContext> ctx_cls(m, "DagContext");
+    ctx_cls
+        .def(py::init<std::vector<Event>, std::unordered_map<std::pair<EventIndex, EventIndex>, Activity, PairHash>,
+                      std::vector<std::pair<EventIndex, Preds>>, double>(),
+             py::arg("events"), py::arg("activities"), py::arg("precedence_list"), py::arg("max_delay"),
+             "Wraps a DAG: events, activity_map, precedence_list, max_delay")
+        .def_readwrite("events", &DagContext::events)
+        .def_readwrite("activities", &DagContext::activity_map)
+        .def_readwrite("precedence_list", &DagContext::precedence_list)
+        .def_readwrite("max_delay", &DagContext::max_delay)
+        .def("__repr__", [](const DagContext& ctx) {
+            return py::str("DagContext(events={}, activities={}, precedence_list={}, max_delay={})")
+                .format(py::repr(py::cast(ctx.events)), py::repr(py::cast(ctx.activity_map)),
+                        py::repr(py::cast(ctx.precedence_list)), ctx.max_delay);
+        });
+
+    // frozen dataclasses, as the reference does at import (_core.cpp:446-488)
+    py::object dataclass_fn = py::module_::import("dataclasses").attr("dataclass");
+    py::dict dc_opts;
+    dc_opts["frozen"] = true;
+    dc_opts["slots"] = true;
+    dc_opts["init"] = false;
+    py::object dataclass = dataclass_fn(**dc_opts);
+    py::module types_mod = py::module_::import("mc_dagprop_b200.types");
+    py::object Second = types_mod.attr("Second");
+    py::dict ts_ann;
+    ts_ann["earliest"] = Second;
+    ts_ann["latest"] = Second;
+    ts_ann["actual"] = Second;
+    ts_cls.attr("__annotations__") = ts_ann;
+    dataclass(ts_cls);
+    py::dict ev_ann;
+    ev_ann["event_id"] = types_mod.attr("EventId");
+    ev_ann["timestamp"] = ts_cls;
+    event_cls.attr("__annotations__") = ev_ann;
+    dataclass(event_cls);
+    py::dict act_ann;
+    act_ann["idx"] = types_mod.attr("ActivityIndex");
+    act_ann["minimal_duration"] = Second;
+    act_ann["activity_type"] = types_mod.attr("ActivityType");
+    activity_cls.attr("__annotations__") = act_ann;
+    dataclass(activity_cls);
+    py::object typing = py::module_::import("typing");
+    py::dict ctx_ann;
+    ctx_ann["events"] = typing.attr("Sequence");
+    ctx_ann["activities"] = typing.attr("Mapping");
+    ctx_ann["precedence_list"] = typing.attr("Sequence");
+    ctx_ann["max_delay"] = Second;
+    ctx_cls.attr("__annotations__") = ctx_ann;
+    dataclass(ctx_cls);
+
+    // SimResult: zero-copy numpy views whose base is the SimResult object (reference _core.cpp:491-516)
+    py::class_<SimResult>(m, "SimResult", py::buffer_protocol())
+        .def_buffer([](SimResult& r) -> py::buffer_info {
+            return py::buffer_info(r.realized(), sizeof(double), py::format_descriptor<double>::format(), 1,
+                                   {r.batch->E}, {sizeof(double)});
+        })
+        .def_property_readonly(
+            "realized", [](const SimResult& r) { return py::array(py::ssize_t(r.batch->E), r.realized(), py::cast(r)); },
+            "Final event times as a NumPy array")
+        .def_property_readonly(
+            "durations", [](const SimResult& r) { return py::array(py::ssize_t(r.batch->A), r.durations(), py::cast(r)); },
+            "Per-link durations (incl. extra) as a NumPy array")
+        .def_property_readonly(
+            "cause_event", [](const SimResult& r) { return py::array(py::ssize_t(r.batch->E), r.cause(), py::cast(r)); },
+            "Index of predecessor causing each event as a NumPy array");
+
+    py::class_<GenericDelayGenerator>(m, "GenericDelayGenerator")
+        .def(py::init<>(), "Create a new delay-generator")
+        .def("set_seed", &GenericDelayGenerator::set_seed, py::arg("seed"), "Set RNG seed for reproducibility")
+        .def("add_constant", &GenericDelayGenerator::add_constant, py::arg("activity_type"), py::arg("factor"),
+             "Constant: delay = factor * duration")
+        .def("add_exponential", &GenericDelayGenerator::add_exponential, py::arg("activity_type"), py::arg("lambda_"),
+             py::arg("max_scale"), "Exponential(lambda) truncated at max_scale")
+        .def("add_gamma", &GenericDelayGenerator::add_gamma, py::arg("activity_type"), py::arg("shape"), py::arg("scale"),
+             py::arg("max_scale") = std::numeric_limits<double>::infinity(), "Gamma(shape,scale) truncated at max_scale")
+        .def(
+            "add_empirical_absolute",
+            [](GenericDelayGenerator& g, ActivityType t, std::vector<double> values, std::vector<double> weights) {
+                g.add_table(MCDP_DIST_EMP_ABS, t, std::move(values), std::move(weights));
+            },
+            py::arg("activity_type"), py::arg("values"), py::arg("weights"),
+            "Empirical absolute: draw one of your provided values, weighted by weights.")
+        .def(
+            "add_empirical_relative",
+            [](GenericDelayGenerator& g, ActivityType t, std::vector<double> factors, std::vector<double> weights) {
+                g.add_table(MCDP_DIST_EMP_REL, t, std::move(factors), std::move(weights));
+            },
+            py::arg("activity_type"), py::arg("factors"), py::arg("weights"),
+            "Empirical relative: draw a factor in [0,inf), then multiply by the activity duration.");
+
+    py::class_<MonteCarloPropagator>(m, "MonteCarloPropagator")
+        .def(py::init<const DagContext&, const GenericDelayGenerator&, int>(), py::arg("context"), py::arg("generator"),
+             py::arg("device") = 0, "Construct simulator with context and delay-generator (device: CUDA ordinal)")
+        .def_static(
+            "from_arrays",
+            [](py::array_t<double, py::array::c_style | py::array::forcecast> earliest,
+               py::array_t<int32_t, py::array::c_style | py::array::forcecast> act_idx,
+               py::array_t<double, py::array::c_style | py::array::forcecast> act_base,
+               py::array_t<int32_t, py::array::c_style | py::array::forcecast> act_type,
+               py::array_t<int32_t, py::array::c_style | py::array::forcecast> prec_target,
+               py::array_t<int64_t, py::array::c_style | py::array::forcecast> prec_off,
+               py::array_t<int32_t, py::array::c_style | py::array::forcecast> pred_src,
+               py::array_t<int32_t, py::array::c_style | py::array::forcecast> pred_act, double max_delay,
+               const GenericDelayGenerator& gen, int device) {
+                return std::make_unique<MonteCarloPropagator>(earliest, act_idx, act_base, act_type, prec_target, prec_off,
+                                                              pred_src, pred_act, max_delay, gen, device);
+            },
+            py::arg("earliest"), py::arg("act_idx"), py::arg("act_base"), py::arg("act_type"), py::arg("prec_target"),
+            py::arg("prec_off"), py::arg("pred_src"), py::arg("pred_act"), py::arg("max_delay"), py::arg("generator"),
+            py::arg("device") = 0, "Construct from flat numpy arrays (no per-object conversion)")
+        .def("node_count", &MonteCarloPropagator::node_count, "Number of events")
+        .def("activity_count", &MonteCarloPropagator::activity_count, "Number of links")
+        .def("level_count", &MonteCarloPropagator::level_count, "Number of topological levels")
+        .def("device", &MonteCarloPropagator::device, "CUDA device ordinal")
+        .def("set_option", &MonteCarloPropagator::set_option, py::arg("option"), py::arg("value"))
+        .def("run", &MonteCarloPropagator::run, py::arg("seed"), "Run single sim")
+        .def("run_many", &MonteCarloPropagator::run_many, py::arg("seeds"), "Run batch sims")
+        .def("run_many_arrays", &MonteCarloPropagator::run_many_arrays, py::arg("seeds"),
+             "Run batch sims, return (realized[n,E], durations[n,A], cause_event[n,E])")
+        .def("run_with_durations", &MonteCarloPropagator::run_with_durations, py::arg("durations"),
+             "Propagate caller-supplied durations[n,A]; returns (realized[n,E], cause_event[n,E])")
+        .def("run_many_reduced", &MonteCarloPropagator::run_many_reduced, py::arg("seeds"),
+             py::arg("thresholds") = std::vector<double>{}, py::arg("n_bins") = 0, py::arg("hist_lo") = 0.0,
+             py::arg("hist_hi") = 1.0, "Per-event statistics of realized - earliest without materialising samples");
+}

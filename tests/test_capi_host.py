@@ -1,0 +1,130 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol include/mcdp_b200.h declares,
+and the host plan compiler (levels, order, tables, validation) behaves -- no compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+from mc_dagprop_b200 import capi, synth
+from mc_dagprop_b200.flat import FlatDag, FlatDists
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mcdp_b200.h")).read()
+    declared = set(re.findall(r"\b(mcdp_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(capi.EXPORTED_SYMBOLS), declared ^ set(capi.EXPORTED_SYMBOLS)
+    lib = capi.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mcdp_abi_version() == 1
+
+
+def test_no_cpu_execution_path():
+    dag, d = synth.c1_toy()
+    plan = capi.Plan(dag, d, device=capi.DEVICE_NONE)
+    with pytest.raises(RuntimeError, match="no CPU execution path"):
+        plan.run_many_host([1, 2, 3])
+    with pytest.raises(RuntimeError, match="no CPU execution path"):
+        plan.run_reduced_host([1, 2, 3])
+    if capi.device_count() == 0:
+        with pytest.raises(RuntimeError, match="CUDA"):
+            capi.Plan(dag, d, device=0)
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (50, 1), (700, 2)])
+def test_plan_order_is_topological_and_levelled(n, seed):
+    dag = synth.random_dag(n, seed)
+    plan = capi.Plan(dag, synth.mixed_small_dists(), device=capi.DEVICE_NONE)
+    osim = oracle.OracleSim(dag, synth.mixed_small_dists())
+    assert (plan.E, plan.A, plan.P) == (osim.E, osim.A, len(osim.csr()[1]))
+    order, level = plan.order()
+    assert sorted(order.tolist()) == list(range(plan.E))
+    pos = np.empty(plan.E, int)
+    pos[order] = np.arange(plan.E)
+    lvl = np.empty(plan.E, int)
+    lvl[order] = level
+    off, src, _ = osim.csr()
+    for e in range(plan.E):
+        preds = src[off[e]:off[e + 1]]
+        assert all(pos[p] < pos[e] for p in preds)
+        # longest-path layering: level = 1 + max level of the predecessors (0 for roots)
+        assert lvl[e] == (1 + max(lvl[p] for p in preds) if len(preds) else 0)
+    assert np.all(np.diff(level) >= 0) and plan.n_levels == (level.max() + 1 if plan.E else 0)
+
+
+def test_plan_cumulative_tables_equal_libstdcpp_discrete_distribution():
+    d = FlatDists()
+    rng = np.random.default_rng(3)
+    w = rng.random(257)
+    d.add_empirical_absolute(1, np.arange(257.0), w)
+    d.add_empirical_relative(2, [1.0, 2.0], [3.0, 1.0])
+    d.add_empirical_absolute(3, [7.0], [2.0])
+    dag = FlatDag.from_precedence_list([0.0, 1.0], [(0, 1.0, 1), (1, 1.0, 2), (2, 1.0, 3)], [(1, [(0, 0)])], 5.0)
+    plan = capi.Plan(dag, d, device=capi.DEVICE_NONE)
+    osim = oracle.OracleSim(dag, d)
+    for t in (1, 2):
+        assert np.array_equal(plan.cumulative(t).view(np.uint64), osim.cumulative(t).view(np.uint64))
+    assert plan.cumulative(3).tolist() == [1.0]  # single entry: index 0 without a draw
+    assert plan.cumulative(99) is None
+
+
+def test_validation_messages_match_reference():
+    d = FlatDists()
+    d.add_constant(1, 0.0)
+    cyc = FlatDag.from_precedence_list([0.0, 0.0], [(0, 1.0, 1), (1, 1.0, 1)], [(1, [(0, 0)]), (0, [(1, 1)])], 1e6)
+    with pytest.raises(RuntimeError, match="Invalid DAG: cycle detected in precedence list"):
+        capi.Plan(cyc, d, device=capi.DEVICE_NONE)
+    ok = FlatDag.from_precedence_list([0.0, 0.0], [(0, 1.0, 1)], [(1, [(0, 0)])], -1.0)
+    with pytest.raises(RuntimeError, match="max_delay must be non-negative"):
+        capi.Plan(ok, d, device=capi.DEVICE_NONE)
+    d2 = FlatDists()
+    d2.add_constant(-1, 0.0)
+    ok.max_delay = 1.0
+    with pytest.raises(RuntimeError, match="Activity type -1 is reserved for no delay"):
+        capi.Plan(ok, d2, device=capi.DEVICE_NONE)
+
+
+def test_validation_of_what_the_reference_leaves_undefined():
+    d = FlatDists()
+    for prec, msg in [([(5, [(0, 0)])], "target"), ([(1, [(7, 0)])], "predecessor"), ([(1, [(0, 9)])], "activity")]:
+        dag = FlatDag.from_precedence_list([0.0, 0.0], [(0, 1.0, 1)], prec, 1.0)
+        with pytest.raises(RuntimeError, match=msg):
+            capi.Plan(dag, d, device=capi.DEVICE_NONE)
+    dag = FlatDag.from_precedence_list([0.0, 0.0], [(0, 1.0, 1)], [(1, [(0, 0)])], 1.0)
+    for bad in (lambda g: g.add_exponential(1, -1.0, 1.0), lambda g: g.add_exponential(1, 1.0, -1.0),
+                lambda g: g.add_gamma(1, 0.0, 1.0), lambda g: g.add_empirical_absolute(1, [], []),
+                lambda g: g.add_empirical_absolute(1, [1.0, 2.0], [0.0, 0.0]),
+                lambda g: g.add_empirical_relative(1, [1.0, 2.0], [1.0, -1.0])):
+        g = FlatDists()
+        bad(g)
+        with pytest.raises(RuntimeError):
+            capi.Plan(dag, g, device=capi.DEVICE_NONE)
+    with pytest.raises(RuntimeError, match="same length"):
+        FlatDists().add_empirical_absolute(1, [1.0, 2.0], [1.0])
+
+
+def test_duplicate_target_entries_last_wins():
+    """reference _core.cpp:240 (preds_by_target[tgt] = entry.second): the last entry's preds win."""
+    dag = FlatDag.from_precedence_list([0.0, 0.0, 0.0], [(0, 10.0, 0), (1, 50.0, 0)],
+                                       [(2, [(0, 0)]), (2, [(1, 1)])], 1e6)
+    plan = capi.Plan(dag, FlatDists(), device=capi.DEVICE_NONE)
+    assert plan.P == 1
+    r, _, c = oracle.OracleSim(dag, FlatDists()).run_many([0])
+    assert r[0, 2] == 50.0 and c[0, 2] == 1
+
+
+def test_benchmark_configs_compile():
+    for gen, (E, A) in [(synth.c1_toy, (10, 12)), (synth.c2_layered, (10_000, 29_700))]:
+        dag, d = gen()
+        plan = capi.Plan(dag, d, device=capi.DEVICE_NONE)
+        assert (plan.E, plan.A) == (E, A)
+    dag, d = synth.c3_network()
+    plan = capi.Plan(dag, d, device=capi.DEVICE_NONE)
+    assert plan.E == 100_000 and 390_000 < plan.A < 410_000 and plan.n_levels == 250
+    dag, d = synth.c5_deep_chain()
+    plan = capi.Plan(dag, d, device=capi.DEVICE_NONE)
+    assert plan.n_levels == 50_001 + 1 - 1 or plan.n_levels >= 50_000
