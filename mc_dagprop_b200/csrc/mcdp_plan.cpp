@@ -208,7 +208,10 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
                 err = "precedence_list: predecessor event index out of range";
                 return false;
             }
-            if (g.pred_act[k] < 0 || g.pred_act[k] >= A) {
+            // An index >= activity_count() reads past actual_durations_ in the reference (its own
+            // LargeScaleTest, test_simulator.py:176-199, relies on that read being 0.0): accepted as
+            // a zero-duration link without a duration row.  Negative indices are rejected.
+            if (g.pred_act[k] < 0) {
                 err = "precedence_list: activity index out of range";
                 return false;
             }
@@ -310,10 +313,16 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
                 PredRec& pr = out.preds[cursor + fan];
                 pr.src_row = uint32_t(g.pred_src[k]);
                 pr.src_event = uint32_t(g.pred_src[k]);
+                pr.pad0 = pr.pad1 = 0;
+                if (g.pred_act[k] >= A) {
+                    pr.act = kNoAct;
+                    pr.base = 0.0;
+                    pr.dist = kNoDist;
+                    continue;
+                }
                 pr.act = uint32_t(g.pred_act[k]);
                 pr.base = base[pr.act];
                 pr.dist = act_dist[pr.act];
-                pr.pad0 = pr.pad1 = 0;
                 act_refs[pr.act]++;
             }
         }

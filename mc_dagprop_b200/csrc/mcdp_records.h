@@ -6,6 +6,7 @@
 namespace mcdp {
 
 constexpr uint32_t kNoDist = 0xFFFFFFFFu;
+constexpr uint32_t kNoAct = 0xFFFFFFFFu;  // precedence entry whose activity index has no duration row
 
 // One event in evaluation order.  `row` is the event's row in the realized/cause arrays
 // (== event id in full/injected mode; a recycled scratch slot in reduced mode).

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ Swee
                 double da, db;
                 if constexpr (MODE == kModeInjected) {
                     double2 dd = make_double2(0.0, 0.0);
-                    if (valid_a) dd = __ldcs(reinterpret_cast<const double2*>(p.inj + size_t(act) * ld + s0));
+                    if (valid_a && act != kNoAct)
+                        dd = __ldcs(reinterpret_cast<const double2*>(p.inj + size_t(act) * ld + s0));
                     da = dd.x;
                     db = dd.y;
                 } else {
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ Swee
                         db = __dadd_rn(base, eb);
                     }
                     if constexpr (MODE == kModeFull) {
-                        if (valid_a)
+                        if (valid_a && act != kNoAct)
                             __stcs(reinterpret_cast<double2*>(p.durations + size_t(act) * ld + s0), make_double2(da, db));
                     }
                 }

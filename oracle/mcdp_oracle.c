@@ -414,7 +414,11 @@ static void or_propagate(const mcdp_or_sim* s, const double* dur, double* realiz
         int32_t c = -1;
         for (int64_t k = s->off[e]; k < s->off[e + 1]; ++k) {
             const int32_t src = s->src[k];
-            double t = realized[src] + dur[s->act[k]];
+            /* An activity index >= activity_count() reads past actual_durations_ in the reference
+             * (undefined behaviour; its own LargeScaleTest, test_simulator.py:176-199, depends on
+             * that read yielding 0.0).  Defined here as a zero-duration link. */
+            const int32_t a = s->act[k];
+            double t = realized[src] + (a < s->A ? dur[a] : 0.0);
             t = (ub < t) ? ub : t;
             if (t >= latest) {
                 latest = t;

@@ -90,7 +90,7 @@ def test_validation_messages_match_reference():
 
 def test_validation_of_what_the_reference_leaves_undefined():
     d = FlatDists()
-    for prec, msg in [([(5, [(0, 0)])], "target"), ([(1, [(7, 0)])], "predecessor"), ([(1, [(0, 9)])], "activity")]:
+    for prec, msg in [([(5, [(0, 0)])], "target"), ([(1, [(7, 0)])], "predecessor"), ([(1, [(0, -2)])], "activity")]:
         dag = FlatDag.from_precedence_list([0.0, 0.0], [(0, 1.0, 1)], prec, 1.0)
         with pytest.raises(RuntimeError, match=msg):
             capi.Plan(dag, d, device=capi.DEVICE_NONE)
@@ -105,6 +105,15 @@ def test_validation_of_what_the_reference_leaves_undefined():
             capi.Plan(dag, g, device=capi.DEVICE_NONE)
     with pytest.raises(RuntimeError, match="same length"):
         FlatDists().add_empirical_absolute(1, [1.0, 2.0], [1.0])
+
+
+def test_activity_index_past_the_end_is_a_zero_duration_link():
+    """The reference reads past actual_durations_ here (UB); its LargeScaleTest relies on 0.0."""
+    dag = FlatDag.from_precedence_list([0.0, 1.0], [(0, 1.0, 1)], [(1, [(0, 9)])], 10.0)
+    plan = capi.Plan(dag, FlatDists(), device=capi.DEVICE_NONE)
+    assert plan.A == 1 and plan.P == 1
+    r, d, c = oracle.OracleSim(dag, FlatDists()).run_many([0])
+    assert r[0].tolist() == [0.0, 1.0] and c[0].tolist() == [-1, -1] and d.shape == (1, 1)
 
 
 def test_duplicate_target_entries_last_wins():

@@ -1,0 +1,288 @@
+"""The reference's own Monte-Carlo tests, ported to run against this package on the B200
+(``-m gpu``).  They use only the public API (``from mc_dagprop import ...``).  Source files:
+reference test/test_simulator.py, test/test_monte_carlo_extra.py, test/test_parity_suite.py,
+test/test_discrete_simulator.py:86-106.  The analytic PMF engine the reference uses as a
+statistical oracle is out of scope here; the exact PMFs of those small scenarios are computed
+in-line by convolution / maximum of discrete distributions."""
+from concurrent.futures import ThreadPoolExecutor
+from itertools import chain
+
+import numpy as np
+import pytest
+
+from mc_dagprop import Activity, DagContext, Event, EventTimestamp, GenericDelayGenerator, MonteCarloPropagator, Simulator
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- test/test_simulator.py --------------------------------------------------------------------
+@pytest.fixture
+def fixture_ctx():
+    events = [Event(str(i), EventTimestamp(e, 100.0, 0.0)) for i, e in enumerate([0.0, 5.0, 10.0, 22.0, 20.0, 100.0])]
+    link_map = {
+        (0, 1): Activity(idx=0, minimal_duration=3.0, activity_type=1),
+        (1, 2): Activity(idx=1, minimal_duration=5.0, activity_type=1),
+        (1, 3): Activity(idx=2, minimal_duration=5.0, activity_type=1),
+        (2, 4): Activity(idx=3, minimal_duration=15.0, activity_type=2),
+        (3, 4): Activity(idx=4, minimal_duration=10.0, activity_type=3),
+    }
+    prec = [(1, [(0, 0)]), (2, [(1, 1)]), (3, [(1, 2)]), (4, [(2, 3), (3, 4)])]
+    return events, link_map, prec, DagContext(events=events, activities=link_map, precedence_list=prec, max_delay=1e6)
+
+
+def test_constant_via_generic(fixture_ctx):
+    ctx = fixture_ctx[3]
+    gen = GenericDelayGenerator()
+    gen.add_constant(activity_type=1, factor=1.0)
+    sim = Simulator(ctx, gen)
+    res = sim.run(seed=7)
+    batch = sim.run_many([1, 2, 3])
+    assert len(batch) == 3 and all(isinstance(b, type(res)) for b in batch)
+    assert res.realized[1] == pytest.approx(6.0) and res.realized[2] == pytest.approx(16.0)
+    assert len(res.durations) == 5 and len(res.realized) == 6 and len(res.cause_event) == 6
+    assert res.cause_event[0] == -1 and res.cause_event[1] == 0 and res.cause_event[2] == 1
+    # result arrays: float64 / float64 / int32 writeable views kept alive by the SimResult
+    assert res.realized.dtype == np.float64 and res.durations.dtype == np.float64 and res.cause_event.dtype == np.int32
+    assert res.realized.base is res and res.realized.flags.writeable
+    assert np.asarray(res).tolist() == res.realized.tolist()  # buffer protocol
+
+
+def test_unsorted_precedence_same_result(fixture_ctx):
+    events, link_map, prec, ctx = fixture_ctx
+    ctx_u = DagContext(events=events, activities=link_map, precedence_list=list(reversed(prec)), max_delay=1e6)
+    ga, gb = GenericDelayGenerator(), GenericDelayGenerator()
+    ga.add_constant(activity_type=1, factor=1.0)
+    gb.add_constant(activity_type=1, factor=1.0)
+    a, b = Simulator(ctx, ga).run(seed=7), Simulator(ctx_u, gb).run(seed=7)
+    np.testing.assert_allclose(a.realized, b.realized)
+    np.testing.assert_allclose(a.durations, b.durations)
+    np.testing.assert_array_equal(a.cause_event, b.cause_event)
+
+
+def test_exponential_via_generic(fixture_ctx):
+    gen = GenericDelayGenerator()
+    gen.add_exponential(1, 1000.0, max_scale=1.0)
+    sim = Simulator(fixture_ctx[3], gen)
+    for res in sim.run_many(tuple(range(3))):
+        r = list(res.realized)
+        assert r[0] == pytest.approx(0.0) and r[1] >= 5.0 and r[2] >= r[1] and r[2] <= r[1] + 50.0 + 1e-6
+        assert len(res.durations) == 5
+        # max_scale = 1 truncation: extra <= base
+        assert res.durations[0] <= 6.0 + 1e-12 and res.durations[1] <= 10.0 + 1e-12
+
+
+def test_propagation(fixture_ctx):
+    gen = GenericDelayGenerator()
+    gen.add_constant(activity_type=1, factor=1.0)
+    gen.add_constant(activity_type=3, factor=3.0)
+    res = Simulator(fixture_ctx[3], gen).run_many(tuple(range(5)))[3]
+    assert res.durations.tolist() == [6.0, 10.0, 10.0, 15.0, 40.0]
+    assert res.realized.tolist() == [0.0, 6.0, 16.0, 22.0, 62.0, 100.0]
+    assert res.cause_event.tolist() == [-1, 0, 1, -1, 3, -1]
+
+
+def test_empirical_support_and_fixed_points(fixture_ctx):
+    """The reference's known-answer values (68.0 / 34.10 / 23.0625 @ seed 7, test_simulator.py:139-172)
+    are tied to the Xoshiro256++ stream; under the Philox contract the same tests hold as support
+    checks: every draw is one of the table values and downstream arithmetic is exact."""
+    gen = GenericDelayGenerator()
+    gen.add_empirical_absolute(activity_type=1, values=[10, 20, 40, 50], weights=[0.1, 0.2, 0.3, 0.4])
+    sim = Simulator(fixture_ctx[3], gen)
+    for res in sim.run_many(range(200)):
+        assert set((res.durations[:3] - np.array([3.0, 5.0, 5.0])).tolist()) <= {10.0, 20.0, 40.0, 50.0}
+        assert res.realized[5] == 100.0
+        assert res.realized[3] == max(22.0, res.realized[1] + res.durations[2])
+    gen = GenericDelayGenerator()
+    gen.add_empirical_relative(activity_type=1, factors=[1.2, 1.3, 1.35, 4.5], weights=[0.1, 0.2, 0.3, 0.4])
+    res = Simulator(fixture_ctx[3], gen).run(seed=7)
+    assert res.durations[0] in [3.0 + f * 3.0 for f in (1.2, 1.3, 1.35, 4.5)] and res.realized[5] == 100.0
+
+
+def test_large_scale_simulation_and_multithreading():
+    n = 10_000
+    events = [Event(str(i), EventTimestamp(float(i), 100.0 + i, 0.0)) for i in range(n)]
+    link_map = {(i, i + 1): Activity(idx=i, minimal_duration=3.0, activity_type=1) for i in range(n - 1)}
+    prec = [(i, [(i - 1, i)]) for i in range(1, n)]
+    ctx = DagContext(events=events, activities=link_map, precedence_list=prec, max_delay=1e6)
+    gen = GenericDelayGenerator()
+    gen.add_constant(activity_type=1, factor=1.0)
+    res = Simulator(ctx, gen).run(seed=7)
+    assert len(res.realized) == n and len(res.durations) == n - 1 and len(res.cause_event) == n
+    assert res.realized[0] == pytest.approx(0.0) and res.realized[n - 1] == pytest.approx(59988.0)
+    batches = 4
+    sims = [Simulator(ctx, gen) for _ in range(batches)]
+    seeds = [[i + j for i in range(1000)] for j in range(batches)]
+    with ThreadPoolExecutor(max_workers=batches) as pool:
+        results = list(chain.from_iterable(pool.map(lambda a: a[0].run_many(a[1]), zip(sims, seeds))))
+    assert len(results) == 4000
+    for r in results[::97]:
+        assert len(r.realized) == n and len(r.durations) == n - 1 and len(r.cause_event) == n
+        assert r.realized[n - 1] == 59988.0
+
+
+# ---- test/test_monte_carlo_extra.py ------------------------------------------------------------
+def _chain_ctx():
+    events = [Event(str(i), EventTimestamp(0.0, 100.0, 0.0)) for i in range(3)]
+    acts = {(0, 1): Activity(idx=0, minimal_duration=1.0, activity_type=1),
+            (1, 2): Activity(idx=1, minimal_duration=2.0, activity_type=1)}
+    return DagContext(events=events, activities=acts, precedence_list=[(1, [(0, 0)]), (2, [(1, 1)])], max_delay=1e6)
+
+
+def test_constant_exponential_gamma_distributions():
+    gen = GenericDelayGenerator()
+    gen.add_constant(activity_type=1, factor=1.0)
+    res = Simulator(_chain_ctx(), gen).run(seed=42)
+    np.testing.assert_allclose(res.durations, [2.0, 4.0])
+    np.testing.assert_allclose(res.realized, [0.0, 2.0, 6.0])
+    for add in (lambda g: g.add_exponential(activity_type=1, lambda_=2.0, max_scale=0.5),
+                lambda g: g.add_gamma(activity_type=1, shape=2.0, scale=1.0, max_scale=0.5)):
+        gen = GenericDelayGenerator()
+        add(gen)
+        for res in Simulator(_chain_ctx(), gen).run_many(range(300)):
+            assert 1.0 <= res.durations[0] <= 1.5 and 2.0 <= res.durations[1] <= 3.0
+            assert res.realized[2] >= res.realized[1]
+
+
+def test_run_many_matches_individual_runs():
+    gen = GenericDelayGenerator()
+    gen.add_exponential(activity_type=1, lambda_=1.0, max_scale=0.5)
+    sim = Simulator(_chain_ctx(), gen)
+    seeds = list(range(5))
+    batch, solo = sim.run_many(seeds), [sim.run(s) for s in seeds]
+    for b, s in zip(batch, solo):
+        np.testing.assert_array_equal(b.realized, s.realized)
+        np.testing.assert_array_equal(b.durations, s.durations)
+        np.testing.assert_array_equal(b.cause_event, s.cause_event)
+    assert sim.run_many([]) == [] and sim.node_count() == 3 and sim.activity_count() == 2
+    # seeds: any iterable of C ints; out-of-range -> TypeError like the reference binding
+    assert len(sim.run_many(range(3))) == 3 and len(sim.run_many(np.arange(3))) == 3
+    assert len(sim.run_many([-1, -2**31, 2**31 - 1])) == 3
+    with pytest.raises(TypeError):
+        sim.run(2**31)
+    with pytest.raises(TypeError):
+        sim.run(1.5)
+
+
+# ---- test/test_parity_suite.py (exact PMFs in-line) --------------------------------------------
+def _pmf_convolve(a, b):
+    return np.convolve(a, b)
+
+
+def _pmf_maximum(a, b):
+    n = max(len(a), len(b))
+    a, b = np.pad(a, (0, n - len(a))), np.pad(b, (0, n - len(b)))
+    ca, cb = np.cumsum(a), np.cumsum(b)
+    cm = ca * cb
+    return np.diff(np.concatenate([[0.0], cm]))
+
+
+def _assert_parity(pmf, samples, p_atol=0.03, m_atol=0.08):
+    idx = np.asarray(samples, dtype=int)
+    counts = np.bincount(idx, minlength=len(pmf))[: len(pmf)]
+    np.testing.assert_allclose(counts / idx.size, pmf, atol=p_atol)
+    assert abs(float(np.mean(samples)) - float(np.dot(np.arange(len(pmf)), pmf))) <= m_atol
+
+
+def _events(n, latest):
+    return [Event(f"E{i}", EventTimestamp(0.0, latest, 0.0)) for i in range(n)]
+
+
+def test_large_chain_parity():
+    pa, pb = np.array([0.1, 0.3, 0.4, 0.2]), np.array([0.15, 0.35, 0.3, 0.2])
+    ctx = DagContext(events=_events(3, 120.0),
+                     activities={(0, 1): Activity(0, 0.0, 1), (1, 2): Activity(1, 0.0, 2)},
+                     precedence_list=[(1, [(0, 0)]), (2, [(1, 1)])], max_delay=120.0)
+    g = GenericDelayGenerator()
+    g.add_empirical_absolute(1, [0.0, 1.0, 2.0, 3.0], pa.tolist())
+    g.add_empirical_absolute(2, [0.0, 1.0, 2.0, 3.0], pb.tolist())
+    sim = MonteCarloPropagator(ctx, g)
+    samples = np.array([r.realized[2] for r in sim.run_many(range(12_000))])
+    _assert_parity(_pmf_convolve(pa, pb), samples)
+
+
+def test_large_branching_parity():
+    pl, pr = np.array([0.15, 0.2, 0.25, 0.25, 0.15]), np.array([0.2, 0.35, 0.3, 0.15])
+    ctx = DagContext(events=_events(4, 200.0),
+                     activities={(0, 1): Activity(0, 0.0, 1), (0, 2): Activity(1, 0.0, 2), (1, 3): Activity(2, 0.0, 2),
+                                 (2, 3): Activity(3, 0.0, 1)},
+                     precedence_list=[(1, [(0, 0)]), (2, [(0, 1)]), (3, [(1, 2), (2, 3)])], max_delay=200.0)
+    g = GenericDelayGenerator()
+    g.add_empirical_absolute(1, [0.0, 1.0, 2.0, 3.0, 4.0], pl.tolist())
+    g.add_empirical_absolute(2, [0.0, 1.0, 2.0, 3.0], pr.tolist())
+    sim = MonteCarloPropagator(ctx, g)
+    samples = np.array([r.realized[3] for r in sim.run_many(range(14_000))])
+    _assert_parity(_pmf_maximum(_pmf_convolve(pl, pr), _pmf_convolve(pr, pl)), samples)
+
+
+def test_many_links_chain_parity():
+    n, p = 100, np.array([0.2, 0.5, 0.3])
+    acts = {(i, i + 1): Activity(idx=i, minimal_duration=0.0, activity_type=1) for i in range(n)}
+    ctx = DagContext(events=_events(n + 1, 1000.0), activities=acts,
+                     precedence_list=[(i + 1, [(i, i)]) for i in range(n)], max_delay=1000.0)
+    g = GenericDelayGenerator()
+    g.add_empirical_absolute(1, [0.0, 1.0, 2.0], p.tolist())
+    sim = MonteCarloPropagator(ctx, g)
+    samples = np.array([sim.run(seed).realized[-1] for seed in range(300)] +
+                       [r.realized[-1] for r in sim.run_many(range(300, 10_000))])
+    pmf = np.array([1.0])
+    for _ in range(n):
+        pmf = _pmf_convolve(pmf, p)
+    _assert_parity(pmf, samples, 0.03, 0.2)
+
+
+def test_max_delay_parity_with_truncation():
+    p = np.array([0.25, 0.25, 0.3, 0.2])  # values 3,4,5,6 from E0 (earliest 10) into E1 (earliest 12), cap 16
+    events = [Event("E0", EventTimestamp(10.0, 100.0, 10.0)), Event("E1", EventTimestamp(12.0, 80.0, 12.0))]
+    ctx = DagContext(events=events, activities={(0, 1): Activity(0, 0.0, 1)}, precedence_list=[(1, [(0, 0)])],
+                     max_delay=4.0)
+    g = GenericDelayGenerator()
+    g.add_empirical_absolute(1, [3.0, 4.0, 5.0, 6.0], p.tolist())
+    sim = MonteCarloPropagator(ctx, g)
+    samples = np.array([r.realized[1] for r in sim.run_many(range(8_000))])
+    assert samples.max() <= 16.0
+    pmf = np.zeros(17)
+    for v, q in zip((13.0, 14.0, 15.0, 16.0), p):
+        pmf[int(v)] += q
+    _assert_parity(pmf, samples, 0.025, 0.05)
+
+
+def test_compare_to_exact_two_link_pmf_and_rootless_cause():
+    """reference test/test_discrete_simulator.py:86-106"""
+    events = [Event(str(i), EventTimestamp(0.0, 10.0, 0.0)) for i in range(3)]
+    ctx = DagContext(events=events, activities={(0, 1): Activity(0, 0.0, 1), (1, 2): Activity(1, 0.0, 2)},
+                     precedence_list=[(1, [(0, 0)]), (2, [(1, 1)])], max_delay=10.0)
+    g = GenericDelayGenerator()
+    g.add_empirical_absolute(1, [1.0, 2.0], [0.5, 0.5])
+    g.add_empirical_absolute(2, [0.0, 1.0], [0.5, 0.5])
+    sim = Simulator(ctx, g)
+    samples = [sim.run(seed=i).realized[2] for i in range(2000)]
+    counts = np.bincount(np.array(samples, dtype=int))[1:4]
+    assert np.allclose(counts / counts.sum(), [0.25, 0.5, 0.25], atol=0.05)
+    assert sim.run(seed=0).cause_event[0] == -1
+
+
+# ---- additive API -------------------------------------------------------------------------------
+def test_additive_array_api_agrees_with_sim_results(fixture_ctx):
+    gen = GenericDelayGenerator()
+    gen.add_gamma(1, 2.0, 0.3, 4.0)
+    gen.add_exponential(2, 0.5, 3.0)
+    sim = Simulator(fixture_ctx[3], gen)
+    seeds = np.arange(50, dtype=np.int32)
+    res = sim.run_many(seeds)
+    r, d, c = sim.run_many_arrays(seeds)
+    assert np.array_equal(r, np.array([x.realized for x in res])) and np.array_equal(d, np.array([x.durations for x in res]))
+    assert np.array_equal(c, np.array([x.cause_event for x in res]))
+    r2, c2 = sim.run_with_durations(d)
+    assert np.array_equal(r2, r) and np.array_equal(c2, c)
+    st = sim.run_many_reduced(seeds, thresholds=[1.0], n_bins=8, hist_lo=0.0, hist_hi=40.0)
+    earliest = np.array([0.0, 5.0, 10.0, 22.0, 20.0, 100.0])
+    np.testing.assert_allclose(st["sum"], (r - earliest).sum(0), rtol=1e-12, atol=1e-9)
+    assert st["hist"].sum() == 50 * 6 and np.array_equal(st["late"][0], ((r - earliest) > 1.0).sum(0))
+    # array ingest builds the same propagator
+    from mc_dagprop_b200.flat import FlatDag
+    fd = FlatDag.from_precedence_list(earliest, [(0, 3.0, 1), (1, 5.0, 1), (2, 5.0, 1), (3, 15.0, 2), (4, 10.0, 3)],
+                                      fixture_ctx[2], 1e6)
+    sim2 = MonteCarloPropagator.from_arrays(fd.earliest, fd.act_idx, fd.act_base, fd.act_type, fd.prec_target,
+                                            fd.prec_off, fd.pred_src, fd.pred_act, fd.max_delay, gen)
+    r3, d3, c3 = sim2.run_many_arrays(seeds)
+    assert np.array_equal(r3, r) and np.array_equal(d3, d) and np.array_equal(c3, c)
