@@ -13,9 +13,9 @@
  * without a usable CUDA device every run call fails with MCDP_ERR_CUDA.
  *
  * Device arrays are event-major, sample-minor: row r (an event or an activity index) of
- * sample column s lives at base[r * ld + s]; ld (elements) must be even and >= n, bases
- * 16-byte aligned, so that one warp reads/writes 64 adjacent samples of a row as 16-byte
- * vectors.  Host arrays of the *_host calls are sample-major ([n][E], [n][A]) exactly like
+ * sample column s lives at base[r * ld + s]; ld (elements) must be a multiple of 64 and >= n
+ * (columns n..ld-1 are padding the kernels may write), bases 16-byte aligned, so that one
+ * warp reads/writes 64 adjacent samples of a row as 16-byte vectors.  Host arrays of the *_host calls are sample-major ([n][E], [n][A]) exactly like
  * the reference's per-sample SimResult vectors (_core.cpp:65-69).
  */
 #ifndef MCDP_B200_H

@@ -221,7 +221,8 @@ SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, 
 
 int32_t check_layout(const void* a, int64_t n, int64_t ld) {
     if (n < 0) return fail(MCDP_ERR_ARG, "n must be non-negative");
-    if (ld < n || (ld & 1)) return fail(MCDP_ERR_ARG, "ld must be even and >= n");
+    if (ld < n || (ld & 63) || ld >= (int64_t(1) << 29))
+        return fail(MCDP_ERR_ARG, "ld must be a multiple of 64, >= n and < 2^29");
     if (reinterpret_cast<uintptr_t>(a) & 15) return fail(MCDP_ERR_ARG, "device buffers must be 16-byte aligned");
     return MCDP_OK;
 }

@@ -51,6 +51,7 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                 r.p[0] = p0;
                 r.p[1] = p1;
                 r.p[2] = std::isinf(p1) ? 1.0 : -std::expm1(-p1 / p0);  // P(x <= max_scale)
+                if (r.p[2] < 0x1p-10) r.flags |= 2;
                 break;
             }
             case MCDP_DIST_GAMMA: {
@@ -70,6 +71,7 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                 r.p[3] = a1;
                 r.p[4] = 1.0 / std::sqrt(9.0 * a1);
                 r.p[5] = 1.0 / p0;
+                r.p[6] = a1 * p1;
                 r.flags = p0 < 1.0 ? 1 : 0;
                 break;
             }

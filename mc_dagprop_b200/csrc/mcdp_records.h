@@ -43,9 +43,10 @@ static_assert(sizeof(OrphanRec) == 16, "OrphanRec must be 16 bytes");
 
 // Distribution parameters, one per activity_type.
 //   CONSTANT     p0 = factor
-//   EXPONENTIAL  p0 = lambda (mean), p1 = max_scale, p2 = F = 1 - exp(-max_scale/lambda)
+//   EXPONENTIAL  p0 = lambda (mean), p1 = max_scale, p2 = F = 1 - exp(-max_scale/lambda);
+//                flags bit1 = F < 2^-10 (series instead of log)
 //   GAMMA        p0 = shape, p1 = scale, p2 = max_scale, p3 = d = shape' - 1/3,
-//                p4 = c = 1/sqrt(9 d), p5 = 1/shape; flags bit0 = shape < 1 (boost)
+//                p4 = c = 1/sqrt(9 d), p5 = 1/shape, p6 = d * scale; flags bit0 = shape < 1 (boost)
 //   EMP_ABS/REL  tab_len entries: cumulative at tab_pool[tab_off .. +len), values at
 //                tab_pool[tab_off+len .. +2 len); guide table guide_pool[guide_off .. + 2^guide_log2)
 struct alignas(16) DistRec {
@@ -56,8 +57,8 @@ struct alignas(16) DistRec {
     int32_t guide_log2;
     int32_t flags;
     int32_t pad0, pad1;
-    double p[6];
+    double p[8];
 };
-static_assert(sizeof(DistRec) == 80, "DistRec must be 80 bytes");
+static_assert(sizeof(DistRec) == 96, "DistRec must be 96 bytes");
 
 }  // namespace mcdp

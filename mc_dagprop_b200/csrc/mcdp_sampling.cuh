@@ -13,6 +13,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "mcdp_math.cuh"
 #include "mcdp_records.h"
 
 namespace mcdp {
@@ -53,11 +54,6 @@ __device__ __forceinline__ double uniform52(uint32_t lo, uint32_t hi) {
     return __hiloint2double(static_cast<int>(0x3FF00000u | khi), static_cast<int>(klo)) - (1.0 - 0x1p-53);
 }
 
-// (w + 0.5) * 2^-32 in (0,1), exact.
-__device__ __forceinline__ double uniform32(uint32_t w) {
-    return __hiloint2double(0x41300000, static_cast<int>(w)) - (1048576.0 - 0x1p-33);
-}
-
 // Table access: SMEM_TABLES => pointers address shared memory (staged copy), else global (L1/L2).
 template <bool SMEM>
 __device__ __forceinline__ double tab_ld(const double* p) {
@@ -84,27 +80,71 @@ __device__ __forceinline__ int emp_index(const DistRec& d, const double* tab, co
     return idx;
 }
 
-// One gamma variate (Marsaglia-Tsang, as libstdc++ random.tcc:2352-2393, normal by Box-Muller
-// from two 32-bit uniforms), truncated to max_scale by continuing the attempt sequence -- the
-// law of the reference's `do x = dist(rng); while (x > max_scale)` loop (_core.cpp:98-104).
-__device__ __forceinline__ double gamma_variate(const DistRec& d, uint32_t seed, uint32_t act, uint32_t key0) {
-    const double scale = d.p[1], mx = d.p[2], a1 = d.p[3], a2 = d.p[4];
-    double x = 0.0;
-    for (uint32_t t = 0; t < kGammaMaxAttempts; ++t) {
-        const Philox4 w = philox4x32_10(seed, act, t, kTagSolo, key0);
-        const double n = sqrt(-2.0 * log(uniform32(w.x))) * cospi(2.0 * uniform32(w.y));
-        double v = 1.0 + a2 * n;
-        if (v <= 0.0) continue;
-        v = v * v * v;
-        const double u = uniform32(w.z);
-        const double n2 = n * n;
-        if (u > 1.0 - 0.0331 * n2 * n2 && log(u) > 0.5 * n2 + a1 * (1.0 - v + log(v))) continue;
-        x = a1 * v * scale;
-        if (d.flags & 1) x *= pow(uniform32(w.w), d.p[5]);
-        if (x > mx) continue;
-        return x;
+// (k + 1/2) * 2^-23 for the top 23 bits k of w: an fp32 uniform strictly inside (0,1), exact.
+__device__ __forceinline__ float uniform23(uint32_t w) {
+    return __uint_as_float(0x3F800000u | (w >> 9)) - (1.0f - 0x1p-24f);
+}
+
+// One Marsaglia-Tsang attempt (libstdc++ random.tcc:2352-2393 restated for SIMT): attempt t of
+// (seed, act) owns one SOLO Philox block.  The normal deviate (Box-Muller) and the two
+// accept/reject comparisons are evaluated with fp32 hardware approximations -- they only steer
+// the draw -- while the variate itself, x = d * v^3 * scale, is formed in fp64.  Returns true
+// when the attempt is accepted and x <= max_scale (the reference's outer `while (x > max_scale)`
+// loop, _core.cpp:98-104, simply continues the attempt sequence).
+__device__ __forceinline__ bool gamma_attempt(const DistRec& d, uint32_t seed, uint32_t act, uint32_t t, uint32_t key0,
+                                              double& x) {
+    const Philox4 w = philox4x32_10(seed, act, t, kTagSolo, key0);
+    const float r2 = -1.3862943611198906f * lg2_approx(uniform23(w.x));           // -2 ln u1
+    const float ang = float(int(w.y)) * 1.4629180792671596e-9f;                    // 2 pi * int32 / 2^32, [-pi, pi)
+    const float nf = sqrt_approx(fmaxf(r2, 0.0f)) * cos_approx(ang);
+    const double n = double(nf);
+    double v = fma(d.p[4], n, 1.0);
+    const bool pos = v > 0.0;
+    v = v * v * v;
+    const float u = uniform23(w.z);
+    const float n2 = nf * nf;
+    bool ok = u <= fmaf(-0.0331f * n2, n2, 1.0f);
+    if (!ok) {
+        const float vf = float(v);
+        const float a1f = float(d.p[3]);
+        // log(u) <= n^2/2 + d (1 - v + log v)
+        ok = 0.6931471805599453f * lg2_approx(u) <= fmaf(0.5f, n2, a1f * (1.0f - vf + 0.6931471805599453f * lg2_approx(vf)));
     }
-    return x > mx ? mx : x;  // attempt cap (the reference would spin forever here)
+    x = d.p[6] * v;  // d * scale * v^3
+    if (d.flags & 1) x *= double(ex2_approx(lg2_approx(uniform23(w.w)) * float(d.p[5])));  // u^(1/shape), shape < 1
+    return pos && ok && x <= d.p[2];
+}
+
+// Gamma variates for the two samples of a thread.  First attempts run straight-line for both
+// samples; afterwards the whole warp iterates a uniform retry loop in which every lane retries one
+// pending sample, so a rejection costs the warp one extra attempt instead of one per sample.
+__device__ __forceinline__ void gamma_variate2(const DistRec& d, uint32_t seed_a, uint32_t seed_b, uint32_t act,
+                                               uint32_t key0, double& xa, double& xb) {
+    bool need_a = !gamma_attempt(d, seed_a, act, 0u, key0, xa);
+    bool need_b = !gamma_attempt(d, seed_b, act, 0u, key0, xb);
+    uint32_t ta = 1u, tb = 1u;
+    while (__any_sync(0xFFFFFFFFu, need_a || need_b)) {
+        const bool do_a = need_a;
+        const uint32_t seed = do_a ? seed_a : seed_b;
+        const uint32_t t = do_a ? ta : tb;
+        double x;
+        const bool ok = gamma_attempt(d, seed, act, t, key0, x);
+        const bool give_up = t + 1u >= kGammaMaxAttempts;  // the reference would spin forever: clamp
+        if (give_up) x = fmin(x, d.p[2]);
+        if (do_a) {
+            ++ta;
+            if (ok || give_up) {
+                xa = x;
+                need_a = false;
+            }
+        } else if (need_b) {
+            ++tb;
+            if (ok || give_up) {
+                xb = x;
+                need_b = false;
+            }
+        }
+    }
 }
 
 // Extra delays of one activity for the two samples a thread owns.  `paired`: the seeds are
@@ -120,8 +160,10 @@ __device__ __forceinline__ void sample_extra2(const DistRec& d, const double* ta
         return;
     }
     if (kind == MCDP_DIST_GAMMA) {
-        ea = __dmul_rn(gamma_variate(d, seed_a, act, key0), base);
-        eb = __dmul_rn(gamma_variate(d, seed_b, act, key0), base);
+        double xa, xb;
+        gamma_variate2(d, seed_a, seed_b, act, key0, xa, xb);
+        ea = __dmul_rn(xa, base);
+        eb = __dmul_rn(xb, base);
         return;
     }
     if ((kind == MCDP_DIST_EMP_ABS || kind == MCDP_DIST_EMP_REL) && d.tab_len < 2) {
@@ -151,8 +193,9 @@ __device__ __forceinline__ void sample_extra2(const DistRec& d, const double* ta
         // inverse CDF of the exponential truncated to [0, max_scale]: the law of the
         // reference's rejection loop (_core.cpp:83-89), without the loop.
         const double lam = d.p[0], mx = d.p[1], F = d.p[2];
-        double xa = -lam * log1p(-ua * F);
-        double xb = -lam * log1p(-ub * F);
+        const bool tiny = d.flags & 2;
+        double xa = lam * neg_log1m(ua * F, tiny);
+        double xb = lam * neg_log1m(ub * F, tiny);
         xa = xa > mx ? mx : xa;
         xb = xb > mx ? mx : xb;
         ea = __dmul_rn(xa, base);

@@ -87,16 +87,15 @@ __global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ Swee
     const int groups_per_cta = (blockDim.x >> 5) / wpg;
     const int64_t group = int64_t(blockIdx.x) * groups_per_cta + group_in_cta;
     if (group * 64 >= p.n) return;  // whole group (all its warps) out of range
+    // ld is a multiple of 64, so every lane of a launched group owns two in-bounds columns; columns
+    // >= n are padding (computed and written like the others, never read back by the host side).
     const int64_t s0 = group * 64 + 2 * lane;
-    const bool valid_a = s0 < p.n;
-    const bool valid_b = s0 + 1 < p.n;
-    const int64_t ld = p.ld;
 
     uint32_t seed_a = 0, seed_b = 1;
     if constexpr (MODE != kModeInjected) {
         if (p.seeds) {
-            if (valid_a) seed_a = uint32_t(__ldg(p.seeds + s0));
-            seed_b = valid_b ? uint32_t(__ldg(p.seeds + s0 + 1)) : seed_a + 1u;
+            seed_a = s0 < p.n ? uint32_t(__ldg(p.seeds + s0)) : 0u;
+            seed_b = s0 + 1 < p.n ? uint32_t(__ldg(p.seeds + s0 + 1)) : seed_a + 1u;
         } else {
             seed_a = uint32_t(p.seed0) + uint32_t(s0);
             seed_b = seed_a + 1u;
@@ -105,33 +104,36 @@ __global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ Swee
     const bool paired = ((seed_a & 1u) == 0u) && (seed_b == seed_a + 1u);
     const uint32_t key0 = p.stream_key;
 
-    double* __restrict__ realized = p.realized;
+    // per-lane column bases; a row is reached with one 32x32->64 multiply-add (ld * 8 < 2^32)
+    const uint32_t ldb8 = uint32_t(p.ld) * 8u, ldb4 = uint32_t(p.ld) * 4u;
+    char* const r_lane = reinterpret_cast<char*>(p.realized) + s0 * 8;
+    char* const d_lane = reinterpret_cast<char*>(p.durations) + s0 * 8;
+    const char* const i_lane = reinterpret_cast<const char*>(p.inj) + s0 * 8;
+    char* const c_lane = reinterpret_cast<char*>(p.cause) + s0 * 4;
 
     for (int lvl = 0; lvl < p.n_levels; ++lvl) {
         const int lb = __ldg(p.level_begin + lvl), le = __ldg(p.level_begin + lvl + 1);
         for (int i = lb + wsub; i < le; i += wpg) {
             const int4 e0 = __ldg(reinterpret_cast<const int4*>(p.events + i));
             const double2 e1 = __ldg(reinterpret_cast<const double2*>(p.events + i) + 1);
-            const uint32_t row = uint32_t(e0.x), pred_begin = uint32_t(e0.z), fan_in = uint32_t(e0.w);
+            const uint32_t row = uint32_t(e0.x), fan_in = uint32_t(e0.w);
+            const PredRec* pr = p.preds + uint32_t(e0.z);
             const double earliest = e1.x, ub = e1.y;
             // _core.cpp:336-337
             double lat_a = earliest, lat_b = earliest;
             int cause_a = -1, cause_b = -1;
-            for (uint32_t k = 0; k < fan_in; ++k) {
-                const PredRec* pr = p.preds + pred_begin + k;
+            for (uint32_t k = 0; k < fan_in; ++k, ++pr) {
                 const int4 q0 = __ldg(reinterpret_cast<const int4*>(pr));
-                const int4 q1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
+                const int2 q1 = __ldg(reinterpret_cast<const int2*>(pr) + 2);
                 const uint32_t src_row = uint32_t(q0.x), act = uint32_t(q0.y);
                 const double base = __hiloint2double(q0.w, q0.z);
                 const uint32_t dist = uint32_t(q1.x);
                 const int src_event = q1.y;
-                double2 rs = make_double2(0.0, 0.0);
-                if (valid_a) rs = *reinterpret_cast<const double2*>(realized + size_t(src_row) * ld + s0);
+                const double2 rs = *reinterpret_cast<const double2*>(r_lane + size_t(src_row) * ldb8);
                 double da, db;
                 if constexpr (MODE == kModeInjected) {
                     double2 dd = make_double2(0.0, 0.0);
-                    if (valid_a && act != kNoAct)
-                        dd = __ldcs(reinterpret_cast<const double2*>(p.inj + size_t(act) * ld + s0));
+                    if (act != kNoAct) dd = __ldcs(reinterpret_cast<const double2*>(i_lane + size_t(act) * ldb8));
                     da = dd.x;
                     db = dd.y;
                 } else {
@@ -144,8 +146,8 @@ __global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ Swee
                         db = __dadd_rn(base, eb);
                     }
                     if constexpr (MODE == kModeFull) {
-                        if (valid_a && act != kNoAct)
-                            __stcs(reinterpret_cast<double2*>(p.durations + size_t(act) * ld + s0), make_double2(da, db));
+                        if (act != kNoAct)
+                            __stcs(reinterpret_cast<double2*>(d_lane + size_t(act) * ldb8), make_double2(da, db));
                     }
                 }
                 // _core.cpp:341-346
@@ -162,12 +164,11 @@ __global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ Swee
             }
             // _core.cpp:348-349
             const double ra = ref_min(lat_a, ub), rb = ref_min(lat_b, ub);
-            if (valid_a) {
-                *reinterpret_cast<double2*>(realized + size_t(row) * ld + s0) = make_double2(ra, rb);
-                if constexpr (MODE != kModeReduced)
-                    __stcs(reinterpret_cast<int2*>(p.cause + size_t(row) * ld + s0), make_int2(cause_a, cause_b));
-            }
+            *reinterpret_cast<double2*>(r_lane + size_t(row) * ldb8) = make_double2(ra, rb);
+            if constexpr (MODE != kModeReduced)
+                __stcs(reinterpret_cast<int2*>(c_lane + size_t(row) * ldb4), make_int2(cause_a, cause_b));
             if constexpr (MODE == kModeReduced) {
+                const bool valid_a = s0 < p.n, valid_b = s0 + 1 < p.n;
                 const uint32_t ev = uint32_t(e0.y);
                 const double xa = valid_a ? ra - earliest : 0.0;
                 const double xb = valid_b ? rb - earliest : 0.0;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ Swee
                 da = __dadd_rn(base, ea);
                 db = __dadd_rn(base, eb);
             }
-            if (valid_a) __stcs(reinterpret_cast<double2*>(p.durations + size_t(act) * ld + s0), make_double2(da, db));
+            __stcs(reinterpret_cast<double2*>(d_lane + size_t(act) * ldb8), make_double2(da, db));
         }
     }
 }

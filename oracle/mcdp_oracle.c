@@ -491,7 +491,7 @@ void mcdp_or_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_
 #define SPEC_GAMMA_MAX_ATTEMPTS 65536u
 
 static double spec_u52(uint64_t x) { return ((double)(x >> 12) + 0.5) * 0x1p-52; }
-static double spec_u32(uint32_t w) { return ((double)w + 0.5) * 0x1p-32; }
+static double spec_u23(uint32_t w) { return ((double)(w >> 9) + 0.5) * 0x1p-23; }
 
 /* 64 random bits of (activity, seed, draw j): one Philox block serves the seed pair {2k, 2k+1} */
 static uint64_t spec_pair_bits(uint32_t act, uint32_t seed, uint32_t j, uint32_t stream_key) {
@@ -527,16 +527,19 @@ static double spec_sample_extra(const or_dist* d, double base, uint32_t act, uin
                 const uint32_t ctr[4] = {seed, act, t, SPEC_TAG_SOLO};
                 uint32_t w[4];
                 mcdp_or_philox4x32_10(ctr, key, w);
-                /* Box-Muller normal from two 32-bit uniforms */
-                const double n = sqrt(-2.0 * log(spec_u32(w[0]))) * cos(6.283185307179586476925286766559 * spec_u32(w[1]));
+                /* Box-Muller normal: radius from a 23-bit uniform, angle 2 pi * int32(w1) / 2^32.  The device
+                 * evaluates this deviate and the two acceptance comparisons with fp32 hardware
+                 * approximations; this restatement is the exact-arithmetic definition. */
+                const double n = sqrt(-2.0 * log(spec_u23(w[0]))) *
+                                 cos(6.283185307179586476925286766559 * (double)(int32_t)w[1] * 0x1p-32);
                 double v = 1.0 + d->a2 * n;
                 if (v <= 0.0) continue;
                 v = v * v * v;
-                const double u = spec_u32(w[2]);
+                const double u = spec_u23(w[2]);
                 const double n2 = n * n;
                 if (u > 1.0 - 0.0331 * n2 * n2 && log(u) > 0.5 * n2 + a1 * (1.0 - v + log(v))) continue;
                 x = a1 * v * d->p1;
-                if (d->p0 != d->malpha) x *= pow(spec_u32(w[3]), 1.0 / d->p0);
+                if (d->p0 != d->malpha) x *= pow(spec_u23(w[3]), 1.0 / d->p0);
                 if (x > d->p2) continue;
                 return x * base;
             }
