@@ -98,10 +98,9 @@ struct mcdp_plan {
     DevBuf<EventRec> d_events;
     DevBuf<PredRec> d_preds;
     DevBuf<int32_t> d_level_begin;
-    DevBuf<OrphanRec> d_orphans;
+    DevBuf<PredRec> d_orphans;
     DevBuf<DistRec> d_dists;
     DevBuf<double> d_tab;
-    DevBuf<uint32_t> d_guide;
     // reduced-mode variant of the stream (rows = recycled scratch slots), built on first use
     DevBuf<EventRec> d_events_red;
     DevBuf<PredRec> d_preds_red;
@@ -127,7 +126,6 @@ struct mcdp_plan {
         d_orphans.release();
         d_dists.release();
         d_tab.release();
-        d_guide.release();
         d_events_red.release();
         d_preds_red.release();
         d_scratch.release();
@@ -159,22 +157,38 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n) {
     LaunchShape s{};
     const int64_t n_groups = (n + 63) / 64;
     int wpg = plan->warps_per_group;
-    if (wpg <= 0) {
-        // enough warps to fill the machine (~16 per SM), but never more than the DAG's levels can feed
-        const int64_t want = (int64_t(plan->sm_count) * 16 + n_groups - 1) / std::max<int64_t>(n_groups, 1);
-        const int64_t avg_width = h.n_levels > 0 ? h.E / h.n_levels : 1;
-        wpg = int(std::max<int64_t>(1, std::min<int64_t>({want, 8, std::max<int64_t>(1, avg_width / 4)})));
-    }
-    wpg = std::max(1, std::min(wpg, 16));
+    constexpr int kMaxWarps = MCDP_MAX_THREADS / 32;
     int gpc = plan->groups_per_cta;
-    if (gpc <= 0) gpc = std::max(1, 4 / wpg);
-    gpc = std::max(1, std::min({gpc, 15, 16 / wpg > 0 ? 16 / wpg : 1}));
+    if (wpg <= 0) {
+        // Candidates: power-of-two warps per group, bounded by what the levels can feed (>= 4 events
+        // per warp per level on average).  Pick the shape that keeps the most warp slots busy over
+        // whole waves (32 warps per SM); ties go to more warps per group: fewer resident samples per
+        // SM shorten the reuse distance of realized rows in L2.
+        const int64_t avg_width = h.n_levels > 0 ? h.E / h.n_levels : 1;
+        const int64_t by_width = std::max<int64_t>(1, avg_width / 4);
+        double best = -1.0;
+        for (int cand = 1; cand <= kMaxWarps && cand <= by_width; cand *= 2) {
+            const int g = gpc > 0 ? std::min(gpc, kMaxWarps / cand) : std::max(1, 8 / cand);
+            const int64_t ctas = (n_groups + g - 1) / g;
+            const int64_t per_sm = std::max(1, 32 / (cand * g));
+            const int64_t slots = int64_t(plan->sm_count) * per_sm;
+            const int64_t waves = (ctas + slots - 1) / slots;
+            const double eff = double(n_groups * cand) / double(waves * plan->sm_count * 32);
+            if (eff >= best - 1e-9) {
+                best = eff;
+                wpg = cand;
+            }
+        }
+        wpg = std::max(wpg, 1);
+    }
+    wpg = std::max(1, std::min(wpg, kMaxWarps));
+    if (gpc <= 0) gpc = std::max(1, 8 / wpg);
+    gpc = std::max(1, std::min({gpc, 15, kMaxWarps / wpg}));
     s.wpg = wpg;
     s.gpc = gpc;
     s.threads = 32 * wpg * gpc;
     s.grid = unsigned((n_groups + gpc - 1) / gpc);
-    const size_t need = sizeof(DistRec) * h.dists.size() + sizeof(double) * h.tab_pool.size() +
-                        sizeof(uint32_t) * h.guide_pool.size();
+    const size_t need = sizeof(DistRec) * h.dists.size() + sizeof(double) * h.tab_pool.size();
     // keep several CTAs per SM resident: stage only when the tables are a modest share of shared memory
     s.smem_tables = need > 0 && need <= std::min<size_t>(plan->smem_optin, 64 * 1024);
     s.smem = s.smem_tables ? need : 0;
@@ -205,14 +219,12 @@ SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, 
     p.orphans = plan->d_orphans.p;
     p.dists = plan->d_dists.p;
     p.tab_pool = plan->d_tab.p;
-    p.guide_pool = plan->d_guide.p;
     p.n = n;
     p.ld = ld;
     p.n_levels = h.n_levels;
     p.n_orphans = int32_t(h.orphans.size());
     p.n_dists = int32_t(h.dists.size());
     p.tab_pool_len = int32_t(h.tab_pool.size());
-    p.guide_pool_len = int32_t(h.guide_pool.size());
     p.E = h.E;
     p.stream_key = plan->stream_key;
     p.warps_per_group = s.wpg;
@@ -323,7 +335,6 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
     if (!rc) rc = upload(plan->d_orphans, h.orphans);
     if (!rc) rc = upload(plan->d_dists, h.dists);
     if (!rc) rc = upload(plan->d_tab, h.tab_pool);
-    if (!rc) rc = upload(plan->d_guide, h.guide_pool);
     if (rc) {
         delete plan;
         return rc;
@@ -339,7 +350,7 @@ int32_t mcdp_plan_set_option(mcdp_plan* plan, int32_t option, int64_t value) {
     switch (option) {
         case MCDP_OPT_STREAM_KEY: plan->stream_key = uint32_t(value); break;
         case MCDP_OPT_WARPS_PER_GROUP:
-            if (value < 0 || value > 16) return fail(MCDP_ERR_ARG, "warps per group must be 0..16");
+            if (value < 0 || value > MCDP_MAX_THREADS / 32) return fail(MCDP_ERR_ARG, "warps per group must be 0..16");
             plan->warps_per_group = int(value);
             break;
         case MCDP_OPT_GROUPS_PER_CTA:
@@ -376,7 +387,8 @@ int64_t mcdp_plan_get_cumulative(const mcdp_plan* plan, int32_t activity_type, d
         if (h.dist_types[i] != activity_type) continue;
         const DistRec& d = h.dists[i];
         if (d.tab_off < 0) return -1;
-        for (int64_t k = 0; k < d.tab_len && k < cap; ++k) cp_out[k] = h.tab_pool[size_t(d.tab_off) + size_t(k)];
+        const size_t cp0 = size_t(d.tab_off) + guide_doubles(uint32_t(d.guide_log2));
+        for (int64_t k = 0; k < d.tab_len && k < cap; ++k) cp_out[k] = h.tab_pool[cp0 + size_t(k)];
         return d.tab_len;
     }
     return -1;

@@ -31,7 +31,7 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
         const int32_t t = last_entry[type];
         DistRec r{};
         r.kind = d.kind[t];
-        r.tab_off = r.guide_off = -1;
+        r.tab_off = -1;
         const double p0 = d.p0[t], p1 = d.p1[t], p2 = d.p2[t];
         switch (r.kind) {
             case MCDP_DIST_CONSTANT:
@@ -82,25 +82,59 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                     err = "empirical distribution needs at least one value";
                     return false;
                 }
-                if (n > (int64_t(1) << 24)) {
+                if (n >= (int64_t(1) << 23)) {
                     err = "empirical distribution table too large";
                     return false;
                 }
                 const double* vals = d.tab_values + d.tab_off[t];
                 const double* w = d.tab_weights + d.tab_off[t];
                 r.tab_len = int32_t(n);
+                // Guide resolution 2^g: the smallest power of two (>= len, <= 16 x len) for which no bucket
+                // [j/G, (j+1)/G) holds more than one cumulative boundary -- then the guide entry plus one
+                // compare-and-step IS the lower bound and the device skips the scan loop.  Tables that
+                // do not reach that within the cap keep the loop (flags bit2 / meta scan bit).
+                int g = 0;
+                bool scan = false;
+                if (n >= 2) {
+                    double sum0 = 0.0;
+                    for (int64_t i = 0; i < n; ++i) sum0 += w[i];
+                    int g0 = 0;
+                    while ((int64_t(1) << g0) < n) ++g0;
+                    const int gmax = std::min(g0 + 4, 20);
+                    g = g0;
+                    for (;; ++g) {
+                        // boundaries are the partial sums; a bucket is clean when consecutive boundaries
+                        // never share floor(cp * G)
+                        const double G = double(int64_t(1) << g);
+                        bool clean = sum0 > 0.0;
+                        double acc = 0.0, prev_bucket = -1.0;
+                        for (int64_t i = 0; i + 1 < n && clean; ++i) {  // the last boundary is 1.0, outside every bucket
+                            acc += w[i] / sum0;
+                            const double b = std::floor(acc * G);
+                            if (b == prev_bucket) clean = false;
+                            prev_bucket = b;
+                        }
+                        if (clean) break;
+                        if (g >= gmax) {
+                            scan = true;
+                            break;
+                        }
+                    }
+                }
+                if (scan) r.flags |= 4;
+                r.guide_log2 = g;
+                const size_t gd = guide_doubles(uint32_t(g));
                 r.tab_off = int32_t(out.tab_pool.size());
-                out.tab_pool.resize(out.tab_pool.size() + 2 * size_t(n));
-                double* cp = out.tab_pool.data() + r.tab_off;
+                out.tab_pool.resize(out.tab_pool.size() + gd + 2 * size_t(n), 0.0);
+                uint32_t* guide = reinterpret_cast<uint32_t*>(out.tab_pool.data() + r.tab_off);
+                double* cp = out.tab_pool.data() + r.tab_off + gd;
                 double* v = cp + n;
                 std::copy(vals, vals + n, v);
                 if (n < 2) {
-                    // std::discrete_distribution with < 2 weights returns 0 without a draw
+                    // std::discrete_distribution with < 2 weights always returns index 0
                     // (libstdc++ random.tcc:2660-2664,2703-2704).
                     cp[0] = 1.0;
-                    r.guide_log2 = 0;
-                    r.guide_off = int32_t(out.guide_pool.size());
-                    out.guide_pool.push_back(0);
+                    guide[0] = 0;
                     break;
                 }
                 // libstdc++ random.tcc:2655-2678: normalise, partial sums, last = 1 -- same
@@ -119,22 +153,18 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                 }
                 double acc = 0.0;
                 for (int64_t i = 0; i < n; ++i) {
-                    const double p = w[i] / sum;
-                    acc = (i == 0) ? p : acc + p;
+                    const double pr = w[i] / sum;
+                    acc = (i == 0) ? pr : acc + pr;
                     cp[i] = acc;
                 }
                 cp[n - 1] = 1.0;
-                // guide table: guide[j] = first i with cp[i] >= j / G, G = 2^g >= n
-                int g = 0;
-                while ((int64_t(1) << g) < n) ++g;
-                r.guide_log2 = g;
-                r.guide_off = int32_t(out.guide_pool.size());
+                // guide[j] = first i with cp[i] >= j / G
                 const int64_t G = int64_t(1) << g;
                 int64_t i = 0;
                 for (int64_t j = 0; j < G; ++j) {
                     const double edge = double(j) / double(G);
                     while (cp[i] < edge) ++i;
-                    out.guide_pool.push_back(uint32_t(i));
+                    guide[j] = uint32_t(i);
                 }
                 break;
             }
@@ -295,6 +325,16 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
         }
     }
 
+    auto fill_dist = [&out](PredRec& pr, uint32_t di) {
+        pr.dist = di;
+        if (di == kNoDist) return;
+        const DistRec& r = out.dists[di];
+        const bool table = r.kind == MCDP_DIST_EMP_ABS || r.kind == MCDP_DIST_EMP_REL;
+        pr.meta = pack_meta(uint32_t(r.kind), table ? uint32_t(r.guide_log2) : 0u, table ? uint32_t(r.tab_len) : 0u,
+                            (r.flags & 4) ? 1u : 0u);
+        pr.tab_off = table ? uint32_t(r.tab_off) : 0u;
+    };
+
     // the stream
     out.events.resize(size_t(E));
     out.preds.resize(size_t(P));
@@ -315,16 +355,17 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
                 PredRec& pr = out.preds[cursor + fan];
                 pr.src_row = uint32_t(g.pred_src[k]);
                 pr.src_event = uint32_t(g.pred_src[k]);
-                pr.pad0 = pr.pad1 = 0;
+                pr.meta = pack_meta(kKindNone, 0, 0);
+                pr.tab_off = 0;
+                pr.dist = kNoDist;
                 if (g.pred_act[k] >= A) {
                     pr.act = kNoAct;
                     pr.base = 0.0;
-                    pr.dist = kNoDist;
                     continue;
                 }
                 pr.act = uint32_t(g.pred_act[k]);
                 pr.base = base[pr.act];
-                pr.dist = act_dist[pr.act];
+                fill_dist(pr, act_dist[pr.act]);
                 act_refs[pr.act]++;
             }
         }
@@ -333,7 +374,14 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
         out.max_fan_in = std::max<int32_t>(out.max_fan_in, int32_t(fan));
     }
     for (int32_t a = 0; a < A; ++a) {
-        if (act_refs[a] == 0) out.orphans.push_back(OrphanRec{uint32_t(a), act_dist[a], base[a]});
+        if (act_refs[a] != 0) continue;
+        PredRec pr{};
+        pr.act = uint32_t(a);
+        pr.base = base[a];
+        pr.meta = pack_meta(kKindNone, 0, 0);
+        pr.dist = kNoDist;
+        fill_dist(pr, act_dist[a]);
+        out.orphans.push_back(pr);
     }
 
     // reduced-mode scratch slots: a slot is released once the LEVEL of the value's last consumer

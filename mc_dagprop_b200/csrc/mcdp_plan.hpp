@@ -22,13 +22,12 @@ struct HostPlan {
     std::vector<EventRec> events;
     std::vector<PredRec> preds;
     std::vector<int32_t> level_begin;  // [n_levels + 1] positions into events
-    std::vector<OrphanRec> orphans;
+    std::vector<PredRec> orphans;      // activities no precedence entry references (src fields unused)
 
     // distributions
     std::vector<DistRec> dists;
     std::vector<int32_t> dist_types;   // activity_type of dists[i]
-    std::vector<double> tab_pool;
-    std::vector<uint32_t> guide_pool;
+    std::vector<double> tab_pool;      // [guide u32 x 2^g][cp][values] blocks
 
     // introspection
     std::vector<int32_t> order;        // event id at each position

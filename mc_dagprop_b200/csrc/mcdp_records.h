@@ -3,6 +3,11 @@
 #pragma once
 #include <cstdint>
 
+#ifndef __CUDACC__
+#define __host__
+#define __device__
+#endif
+
 namespace mcdp {
 
 constexpr uint32_t kNoDist = 0xFFFFFFFFu;
@@ -22,24 +27,31 @@ struct alignas(16) EventRec {
 };
 static_assert(sizeof(EventRec) == 32, "EventRec must be 32 bytes");
 
-// One precedence entry (src event --activity--> this event), in the caller's order.
+// One precedence entry (src event --activity--> this event), in the caller's order.  Everything the
+// sampler needs to dispatch is in the record itself (`meta`, `tab_off`), so the kind switch and the
+// table lookup do not wait on a dependent DistRec load.
+//   meta = kind << 29 | guide_log2 << 24 | scan << 23 | table_len      (kind 7 = no distribution;
+//          scan = 1 when a guide bucket may hold more than one cumulative boundary)
+//   tab_off: table block in the pool, in 8-byte units: [guide: 2^g u32][cp: len f64][values: len f64]
 struct alignas(16) PredRec {
     uint32_t src_row;
     uint32_t act;
     double base;        // Activity.minimal_duration
-    uint32_t dist;      // index into DistRec[], kNoDist = duration is `base`
+    uint32_t meta;
+    uint32_t tab_off;
     uint32_t src_event; // value written to cause_event
-    uint32_t pad0, pad1;
+    uint32_t dist;      // index into DistRec[] (parameters of constant / exponential / gamma), kNoDist = none
 };
 static_assert(sizeof(PredRec) == 32, "PredRec must be 32 bytes");
 
-// An activity that no precedence entry references: sampled and written, never propagated.
-struct alignas(16) OrphanRec {
-    uint32_t act;
-    uint32_t dist;
-    double base;
-};
-static_assert(sizeof(OrphanRec) == 16, "OrphanRec must be 16 bytes");
+constexpr uint32_t kKindNone = 7u;
+__host__ __device__ inline uint32_t pack_meta(uint32_t kind, uint32_t guide_log2, uint32_t len, uint32_t scan = 0) {
+    return (kind << 29) | (guide_log2 << 24) | (scan << 23) | (len & 0x7FFFFFu);
+}
+__host__ __device__ inline uint32_t guide_doubles(uint32_t guide_log2) {
+    const uint32_t g = 1u << guide_log2;
+    return g >= 2u ? g / 2u : 1u;
+}
 
 // Distribution parameters, one per activity_type.
 //   CONSTANT     p0 = factor
@@ -47,16 +59,14 @@ static_assert(sizeof(OrphanRec) == 16, "OrphanRec must be 16 bytes");
 //                flags bit1 = F < 2^-10 (series instead of log)
 //   GAMMA        p0 = shape, p1 = scale, p2 = max_scale, p3 = d = shape' - 1/3,
 //                p4 = c = 1/sqrt(9 d), p5 = 1/shape, p6 = d * scale; flags bit0 = shape < 1 (boost)
-//   EMP_ABS/REL  tab_len entries: cumulative at tab_pool[tab_off .. +len), values at
-//                tab_pool[tab_off+len .. +2 len); guide table guide_pool[guide_off .. + 2^guide_log2)
+//   EMP_ABS/REL  tab_len entries in the pool block at tab_off (see PredRec)
 struct alignas(16) DistRec {
     int32_t kind;
     int32_t tab_len;
     int32_t tab_off;
-    int32_t guide_off;
     int32_t guide_log2;
-    int32_t flags;
-    int32_t pad0, pad1;
+    int32_t flags;      // bit0 gamma shape < 1, bit1 exponential series, bit2 table needs the scan loop
+    int32_t pad0, pad1, pad2;
     double p[8];
 };
 static_assert(sizeof(DistRec) == 96, "DistRec must be 96 bytes");

@@ -54,7 +54,7 @@ __device__ __forceinline__ double uniform52(uint32_t lo, uint32_t hi) {
     return __hiloint2double(static_cast<int>(0x3FF00000u | khi), static_cast<int>(klo)) - (1.0 - 0x1p-53);
 }
 
-// Table access: SMEM_TABLES => pointers address shared memory (staged copy), else global (L1/L2).
+// Table access: SMEM => the pool pointer addresses shared memory (staged copy), else global (L1/L2).
 template <bool SMEM>
 __device__ __forceinline__ double tab_ld(const double* p) {
     if constexpr (SMEM) return *p;
@@ -67,16 +67,18 @@ __device__ __forceinline__ uint32_t guide_ld(const uint32_t* p) {
 }
 
 // Inverse-CDF lookup with std::lower_bound semantics (first cp[i] >= u; libstdc++
-// random.tcc:2709-2713) through a guide table: start at guide[top bits of u], then scan.
+// random.tcc:2709-2713): the guide table (four buckets per entry) gives the first candidate, one
+// unconditional compare-and-step follows, and a scan loop that almost never iterates finishes.
 template <bool SMEM>
-__device__ __forceinline__ int emp_index(const DistRec& d, const double* tab, const uint32_t* guide, uint32_t lo,
-                                         uint32_t hi, double u) {
-    // floor(u * 2^g) == (X >> 12) >> (52 - g) == hi >> (32 - g)   (g <= 24)
-    const uint32_t j = d.guide_log2 ? (hi >> (32 - d.guide_log2)) : 0u;
-    (void)lo;
-    int idx = static_cast<int>(guide_ld<SMEM>(guide + d.guide_off + j));
-    const double* cp = tab + d.tab_off;
-    while (tab_ld<SMEM>(cp + idx) < u) ++idx;  // cp[len-1] == 1.0 > u terminates the scan
+__device__ __forceinline__ int emp_index(const uint32_t* guide, const double* cp, uint32_t g, bool scan, uint32_t hi,
+                                         double u) {
+    // floor(u * 2^g) == (X >> 12) >> (52 - g) == hi >> (32 - g)
+    const uint32_t j = g ? (hi >> (32u - g)) : 0u;
+    int idx = static_cast<int>(guide_ld<SMEM>(guide + j));
+    idx += tab_ld<SMEM>(cp + idx) < u;  // cp[len-1] == 1.0 > u: never steps past the end
+    if (scan) {                         // only tables whose guide buckets may hold several boundaries
+        while (tab_ld<SMEM>(cp + idx) < u) ++idx;
+    }
     return idx;
 }
 
@@ -147,29 +149,24 @@ __device__ __forceinline__ void gamma_variate2(const DistRec& d, uint32_t seed_a
     }
 }
 
-// Extra delays of one activity for the two samples a thread owns.  `paired`: the seeds are
-// {2k, 2k+1}, so one PAIR block serves both.  Returns extra (the value Dist::sample returns);
-// the caller forms base + extra with separately rounded operations like the reference build.
+// Extra delays of one activity for the two samples a thread owns.  `meta`/`tab_off` come from the
+// precedence record (kind, guide bits, table length / pool block).  `paired`: the seeds are
+// {2k, 2k+1}, so one PAIR block serves both.  Returns extra (the value Dist::sample returns); the
+// caller forms base + extra with separately rounded operations like the reference build.
 template <bool SMEM>
-__device__ __forceinline__ void sample_extra2(const DistRec& d, const double* tab, const uint32_t* guide, double base,
-                                              uint32_t act, uint32_t seed_a, uint32_t seed_b, bool paired,
-                                              uint32_t key0, double& ea, double& eb) {
-    const int kind = d.kind;
+__device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, const DistRec* dists, uint32_t dist,
+                                              const double* tab, double base, uint32_t act, uint32_t seed_a,
+                                              uint32_t seed_b, bool paired, uint32_t key0, double& ea, double& eb) {
+    const uint32_t kind = meta >> 29;
     if (kind == MCDP_DIST_CONSTANT) {
-        ea = eb = __dmul_rn(base, d.p[0]);  // _core.cpp:75
+        ea = eb = __dmul_rn(base, dists[dist].p[0]);  // _core.cpp:75
         return;
     }
     if (kind == MCDP_DIST_GAMMA) {
         double xa, xb;
-        gamma_variate2(d, seed_a, seed_b, act, key0, xa, xb);
+        gamma_variate2(dists[dist], seed_a, seed_b, act, key0, xa, xb);
         ea = __dmul_rn(xa, base);
         eb = __dmul_rn(xb, base);
-        return;
-    }
-    if ((kind == MCDP_DIST_EMP_ABS || kind == MCDP_DIST_EMP_REL) && d.tab_len < 2) {
-        // < 2 weights: index 0 without consuming a draw (libstdc++ random.tcc:2703-2704)
-        const double v = tab_ld<SMEM>(tab + d.tab_off + d.tab_len);
-        ea = eb = (kind == MCDP_DIST_EMP_ABS) ? v : __dmul_rn(v, base);
         return;
     }
     // one 64-bit draw per sample
@@ -192,6 +189,7 @@ __device__ __forceinline__ void sample_extra2(const DistRec& d, const double* ta
     if (kind == MCDP_DIST_EXPONENTIAL) {
         // inverse CDF of the exponential truncated to [0, max_scale]: the law of the
         // reference's rejection loop (_core.cpp:83-89), without the loop.
+        const DistRec& d = dists[dist];
         const double lam = d.p[0], mx = d.p[1], F = d.p[2];
         const bool tiny = d.flags & 2;
         double xa = lam * neg_log1m(ua * F, tiny);
@@ -202,9 +200,17 @@ __device__ __forceinline__ void sample_extra2(const DistRec& d, const double* ta
         eb = __dmul_rn(xb, base);
         return;
     }
-    const double* vals = tab + d.tab_off + d.tab_len;
-    const double va = tab_ld<SMEM>(vals + emp_index<SMEM>(d, tab, guide, lo_a, hi_a, ua));
-    const double vb = tab_ld<SMEM>(vals + emp_index<SMEM>(d, tab, guide, lo_b, hi_b, ub));
+    // empirical tables: pool block = [guide u32 x 2^g][cp f64 x len][values f64 x len]
+    const uint32_t g = (meta >> 24) & 31u, len = meta & 0x7FFFFFu;
+    const bool scan = meta & 0x800000u;
+    const double* blk = tab + tab_off;
+    const uint32_t* guide = reinterpret_cast<const uint32_t*>(blk);
+    const double* cp = blk + guide_doubles(g);
+    const double* vals = cp + len;
+    const int ia = emp_index<SMEM>(guide, cp, g, scan, hi_a, ua);
+    const int ib = emp_index<SMEM>(guide, cp, g, scan, hi_b, ub);
+    const double va = tab_ld<SMEM>(vals + ia);
+    const double vb = tab_ld<SMEM>(vals + ib);
     if (kind == MCDP_DIST_EMP_ABS) {  // _core.cpp:125
         ea = va;
         eb = vb;

@@ -15,16 +15,24 @@
 
 namespace mcdp {
 
+// CTA shape: at most 16 warps (groups_per_cta x warps_per_group), two such CTAs per SM => 64
+// registers per thread and 32 resident warps per SM.
+#ifndef MCDP_MAX_THREADS
+#define MCDP_MAX_THREADS 512
+#endif
+#ifndef MCDP_MIN_BLOCKS
+#define MCDP_MIN_BLOCKS 2
+#endif
+
 enum SweepMode { kModeFull = 0, kModeInjected = 1, kModeReduced = 2 };
 
 struct SweepParams {
     const EventRec* events;
     const PredRec* preds;
     const int32_t* level_begin;
-    const OrphanRec* orphans;
+    const PredRec* orphans;
     const DistRec* dists;
     const double* tab_pool;
-    const uint32_t* guide_pool;
     const int32_t* seeds;  // nullptr => seed0 + sample index
     double* realized;      // [rows][ld]  (output in full/injected mode, scratch in reduced mode)
     double* durations;     // [A][ld]     full mode: written
@@ -37,7 +45,7 @@ struct SweepParams {
     double thresholds[MCDP_MAX_THRESHOLDS];
     double hist_lo, hist_scale;
     int64_t n, ld;
-    int32_t n_levels, n_orphans, n_dists, tab_pool_len, guide_pool_len;
+    int32_t n_levels, n_orphans, n_dists, tab_pool_len;
     int32_t n_thresholds, n_bins, E;
     int32_t seed0;
     uint32_t stream_key;
@@ -58,25 +66,21 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ double ref_min(double a, double b) { return (b < a) ? b : a; }
 
 template <int MODE, bool SMEM>
-__global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ SweepParams p) {
+__global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kernel(const __grid_constant__ SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DistRec* dists = p.dists;
     const double* tab = p.tab_pool;
-    const uint32_t* guide = p.guide_pool;
     if constexpr (SMEM) {
         // stage distribution records + inverse-CDF tables + guide tables once per CTA
         DistRec* s_dists = reinterpret_cast<DistRec*>(smem_raw);
         double* s_tab = reinterpret_cast<double*>(smem_raw + sizeof(DistRec) * p.n_dists);
-        uint32_t* s_guide = reinterpret_cast<uint32_t*>(s_tab + p.tab_pool_len);
         const int n16 = int(sizeof(DistRec) / 16) * p.n_dists;
         for (int i = threadIdx.x; i < n16; i += blockDim.x)
             reinterpret_cast<int4*>(s_dists)[i] = __ldg(reinterpret_cast<const int4*>(p.dists) + i);
         for (int i = threadIdx.x; i < p.tab_pool_len; i += blockDim.x) s_tab[i] = __ldg(p.tab_pool + i);
-        for (int i = threadIdx.x; i < p.guide_pool_len; i += blockDim.x) s_guide[i] = __ldg(p.guide_pool + i);
         __syncthreads();
         dists = s_dists;
         tab = s_tab;
-        guide = s_guide;
     }
 
     const int lane = threadIdx.x & 31;
@@ -111,9 +115,35 @@ __global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ Swee
     const char* const i_lane = reinterpret_cast<const char*>(p.inj) + s0 * 8;
     char* const c_lane = reinterpret_cast<char*>(p.cause) + s0 * 4;
 
+    // Level scheduling.  One warp per group: events in stream order, no synchronisation.  Several
+    // warps per group: the warps of a group pull event positions from a shared-memory counter (one
+    // per level parity; the idle one is re-armed for the next level while the current level runs),
+    // so uneven fan-in or memory latency does not leave warps waiting at the level barrier.
+    __shared__ int s_cursor[16][2];
+    const bool dyn = wpg > 1;
+    if (dyn) {
+        if (wsub == 0 && lane == 0) s_cursor[group_in_cta][0] = 0;
+        group_barrier(1 + group_in_cta, wpg * 32);
+    }
+    auto grab = [&](int parity) -> int {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(&s_cursor[group_in_cta][parity], 1);
+        return __shfl_sync(0xFFFFFFFFu, v, 0);
+    };
+
     for (int lvl = 0; lvl < p.n_levels; ++lvl) {
         const int lb = __ldg(p.level_begin + lvl), le = __ldg(p.level_begin + lvl + 1);
-        for (int i = lb + wsub; i < le; i += wpg) {
+        const int par = lvl & 1;
+        int i_next;
+        if (dyn) {
+            if (wsub == 0 && lane == 0) s_cursor[group_in_cta][par ^ 1] = le;  // next level starts at le
+            i_next = grab(par);
+        } else {
+            i_next = lb;
+        }
+        while (i_next < le) {
+            const int i = i_next;
+            i_next = dyn ? grab(par) : i + 1;
             const int4 e0 = __ldg(reinterpret_cast<const int4*>(p.events + i));
             const double2 e1 = __ldg(reinterpret_cast<const double2*>(p.events + i) + 1);
             const uint32_t row = uint32_t(e0.x), fan_in = uint32_t(e0.w);
@@ -122,14 +152,28 @@ __global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ Swee
             // _core.cpp:336-337
             double lat_a = earliest, lat_b = earliest;
             int cause_a = -1, cause_b = -1;
-            for (uint32_t k = 0; k < fan_in; ++k, ++pr) {
-                const int4 q0 = __ldg(reinterpret_cast<const int4*>(pr));
-                const int2 q1 = __ldg(reinterpret_cast<const int2*>(pr) + 2);
-                const uint32_t src_row = uint32_t(q0.x), act = uint32_t(q0.y);
+            // rolling prefetch: the next entry's record and predecessor row are requested before the
+            // current entry's delay is drawn, so their latency hides behind the sampling arithmetic
+            int4 nq0 = make_int4(0, 0, 0, 0), nq1 = make_int4(0, 0, 0, 0);
+            double2 nrs = make_double2(0.0, 0.0);
+            if (fan_in) {
+                nq0 = __ldg(reinterpret_cast<const int4*>(pr));
+                nq1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
+                nrs = *reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(nq0.x)) * ldb8);
+            }
+            for (uint32_t k = 0; k < fan_in; ++k) {
+                const int4 q0 = nq0, q1 = nq1;
+                const double2 rs = nrs;
+                ++pr;
+                if (k + 1 < fan_in) {
+                    nq0 = __ldg(reinterpret_cast<const int4*>(pr));
+                    nq1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
+                    nrs = *reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(nq0.x)) * ldb8);
+                }
+                const uint32_t act = uint32_t(q0.y);
                 const double base = __hiloint2double(q0.w, q0.z);
-                const uint32_t dist = uint32_t(q1.x);
-                const int src_event = q1.y;
-                const double2 rs = *reinterpret_cast<const double2*>(r_lane + size_t(src_row) * ldb8);
+                const uint32_t meta = uint32_t(q1.x);
+                const int src_event = q1.z;
                 double da, db;
                 if constexpr (MODE == kModeInjected) {
                     double2 dd = make_double2(0.0, 0.0);
@@ -137,11 +181,12 @@ __global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ Swee
                     da = dd.x;
                     db = dd.y;
                 } else {
-                    if (dist == kNoDist) {
+                    if ((meta >> 29) == kKindNone) {
                         da = db = base;  // _core.cpp:304-305,325
                     } else {
                         double ea, eb;
-                        sample_extra2<SMEM>(dists[dist], tab, guide, base, act, seed_a, seed_b, paired, key0, ea, eb);
+                        sample_extra2<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, seed_a, seed_b,
+                                            paired, key0, ea, eb);
                         da = __dadd_rn(base, ea);  // _core.cpp:328
                         db = __dadd_rn(base, eb);
                     }
@@ -204,19 +249,21 @@ __global__ void __launch_bounds__(512) sweep_kernel(const __grid_constant__ Swee
                 }
             }
         }
-        if (wpg > 1) group_barrier(1 + group_in_cta, wpg * 32);
+        if (dyn) group_barrier(1 + group_in_cta, wpg * 32);
     }
 
     if constexpr (MODE == kModeFull) {
         // activities no precedence entry references still get their sampled duration (_core.cpp:323-329)
         for (int i = wsub; i < p.n_orphans; i += wpg) {
-            const int4 o = __ldg(reinterpret_cast<const int4*>(p.orphans + i));
-            const uint32_t act = uint32_t(o.x), dist = uint32_t(o.y);
-            const double base = __hiloint2double(o.w, o.z);
+            const int4 q0 = __ldg(reinterpret_cast<const int4*>(p.orphans + i));
+            const int4 q1 = __ldg(reinterpret_cast<const int4*>(p.orphans + i) + 1);
+            const uint32_t act = uint32_t(q0.y), meta = uint32_t(q1.x);
+            const double base = __hiloint2double(q0.w, q0.z);
             double da = base, db = base;
-            if (dist != kNoDist) {
+            if ((meta >> 29) != kKindNone) {
                 double ea, eb;
-                sample_extra2<SMEM>(dists[dist], tab, guide, base, act, seed_a, seed_b, paired, key0, ea, eb);
+                sample_extra2<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, seed_a, seed_b, paired,
+                                    key0, ea, eb);
                 da = __dadd_rn(base, ea);
                 db = __dadd_rn(base, eb);
             }

@@ -34,11 +34,11 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "c2"
     if which == "c2":
         dag, d = synth.c2_layered()
-        for n in (65536, 262144):
-            for wpg, gpc in ((1, 4), (1, 8), (2, 2), (4, 1), (4, 2)):
+        for n in (262144,):
+            for wpg, gpc in ((8, 1), (16, 1), (0, 0)):
                 run("c2", dag, d, n, wpg, gpc)
     elif which == "c3":
         dag, d = synth.c3_network()
-        for n in (16384, 32768):
-            for wpg, gpc in ((2, 2), (4, 1), (4, 2), (8, 1), (8, 2), (16, 1)):
+        for n in (18944,):
+            for wpg, gpc in ((16, 1), (0, 0)):
                 run("c3", dag, d, n, wpg, gpc)
