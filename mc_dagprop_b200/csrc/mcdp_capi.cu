@@ -226,7 +226,7 @@ SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, 
     p.n_dists = int32_t(h.dists.size());
     p.tab_pool_len = int32_t(h.tab_pool.size());
     p.E = h.E;
-    p.stream_key = plan->stream_key;
+    for (int r = 0; r < 10; ++r) p.keys.k[r] = plan->stream_key + uint32_t(r) * 0x9E3779B9u;
     p.warps_per_group = s.wpg;
     return p;
 }

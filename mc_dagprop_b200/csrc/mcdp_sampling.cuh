@@ -6,7 +6,7 @@
 // result of a sample does not depend on which thread, chunk or GPU computes it and the
 // activities can be drawn in evaluation order, fused with the max-plus sweep.
 //
-//   key     = (stream_key, 'MCDP')                     -- kernel-uniform: round keys fold to constants
+//   key     = (stream_key, 'MCDP')                     -- round keys precomputed, read as constant operands
 //   PAIR    ctr = (seed >> 1, act, j, 'PAIR')          -- one block serves seeds {2k, 2k+1}: 64 bits each
 //   SOLO    ctr = (seed,      act, t, 'SOLO')          -- gamma attempt t: 4 x 32 bits
 #pragma once
@@ -27,21 +27,34 @@ struct Philox4 {
     uint32_t x, y, z, w;
 };
 
-// Philox4x32-10 (Salmon et al., SC'11).  key0 is kernel-uniform, so ptxas keeps the ten round
-// keys in uniform registers; per block this is 20 IMAD.WIDE + 20 LOP3.
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t key0) {
-    uint32_t k0 = key0, k1 = kKey1;
+// 32 x 32 -> (hi, lo).  Written as mul.wide + register-pair unpack: the plain C form
+// `uint64_t p = (uint64_t)a * b; hi = p >> 32` makes ptxas 12.9 add a zero-valued uniform register
+// to every high word (one extra VIADD per multiply, +50% on the whole generator).
+__device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+    asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0,%1}, p;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+
+// The ten Philox round keys of word 0, key0 + r * 0x9E3779B9, precomputed on the host: they arrive
+// through the kernel parameter block, so each round's XOR reads its key as a constant-bank operand.
+struct PhiloxKeys {
+    uint32_t k[10];
+};
+
+// Philox4x32-10 (Salmon et al., SC'11): per block 20 IMAD.WIDE + 20 LOP3.
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 const PhiloxKeys& key0) {
+    uint32_t k1 = kKey1;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c0;
-        const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c2;
-        const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c3 ^ k1;
-        c1 = static_cast<uint32_t>(p1);
-        c3 = static_cast<uint32_t>(p0);
+        uint32_t h0, l0, h1, l1;
+        mulhilo32(0xD2511F53u, c0, h0, l0);
+        mulhilo32(0xCD9E8D57u, c2, h1, l1);
+        const uint32_t n0 = h1 ^ c1 ^ key0.k[r];
+        const uint32_t n2 = h0 ^ c3 ^ k1;
+        c1 = l1;
+        c3 = l0;
         c0 = n0;
         c2 = n2;
-        k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
     return Philox4{c0, c1, c2, c3};
@@ -93,8 +106,8 @@ __device__ __forceinline__ float uniform23(uint32_t w) {
 // the draw -- while the variate itself, x = d * v^3 * scale, is formed in fp64.  Returns true
 // when the attempt is accepted and x <= max_scale (the reference's outer `while (x > max_scale)`
 // loop, _core.cpp:98-104, simply continues the attempt sequence).
-__device__ __forceinline__ bool gamma_attempt(const DistRec& d, uint32_t seed, uint32_t act, uint32_t t, uint32_t key0,
-                                              double& x) {
+__device__ __forceinline__ bool gamma_attempt(const DistRec& d, uint32_t seed, uint32_t act, uint32_t t,
+                                              const PhiloxKeys& key0, double& x) {
     const Philox4 w = philox4x32_10(seed, act, t, kTagSolo, key0);
     const float r2 = -1.3862943611198906f * lg2_approx(uniform23(w.x));           // -2 ln u1
     const float ang = float(int(w.y)) * 1.4629180792671596e-9f;                    // 2 pi * int32 / 2^32, [-pi, pi)
@@ -121,7 +134,7 @@ __device__ __forceinline__ bool gamma_attempt(const DistRec& d, uint32_t seed, u
 // samples; afterwards the whole warp iterates a uniform retry loop in which every lane retries one
 // pending sample, so a rejection costs the warp one extra attempt instead of one per sample.
 __device__ __forceinline__ void gamma_variate2(const DistRec& d, uint32_t seed_a, uint32_t seed_b, uint32_t act,
-                                               uint32_t key0, double& xa, double& xb) {
+                                               const PhiloxKeys& key0, double& xa, double& xb) {
     bool need_a = !gamma_attempt(d, seed_a, act, 0u, key0, xa);
     bool need_b = !gamma_attempt(d, seed_b, act, 0u, key0, xb);
     uint32_t ta = 1u, tb = 1u;
@@ -156,7 +169,8 @@ __device__ __forceinline__ void gamma_variate2(const DistRec& d, uint32_t seed_a
 template <bool SMEM>
 __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, const DistRec* dists, uint32_t dist,
                                               const double* tab, double base, uint32_t act, uint32_t seed_a,
-                                              uint32_t seed_b, bool paired, uint32_t key0, double& ea, double& eb) {
+                                              uint32_t seed_b, bool paired, const PhiloxKeys& key0, double& ea,
+                                              double& eb) {
     const uint32_t kind = meta >> 29;
     if (kind == MCDP_DIST_CONSTANT) {
         ea = eb = __dmul_rn(base, dists[dist].p[0]);  // _core.cpp:75

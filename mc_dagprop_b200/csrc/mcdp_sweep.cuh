@@ -48,7 +48,7 @@ struct SweepParams {
     int32_t n_levels, n_orphans, n_dists, tab_pool_len;
     int32_t n_thresholds, n_bins, E;
     int32_t seed0;
-    uint32_t stream_key;
+    PhiloxKeys keys;  // round keys of Philox key word 0 (stream_key + r * 0x9E3779B9)
     int32_t warps_per_group;
 };
 
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
         }
     }
     const bool paired = ((seed_a & 1u) == 0u) && (seed_b == seed_a + 1u);
-    const uint32_t key0 = p.stream_key;
+    const PhiloxKeys& key0 = p.keys;
 
     // per-lane column bases; a row is reached with one 32x32->64 multiply-add (ld * 8 < 2^32)
     const uint32_t ldb8 = uint32_t(p.ld) * 8u, ldb4 = uint32_t(p.ld) * 4u;
