@@ -226,6 +226,7 @@ SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, 
     p.n_dists = int32_t(h.dists.size());
     p.tab_pool_len = int32_t(h.tab_pool.size());
     p.E = h.E;
+    p.max_delay = h.max_delay;
     for (int r = 0; r < 10; ++r) p.keys.k[r] = plan->stream_key + uint32_t(r) * 0x9E3779B9u;
     p.warps_per_group = s.wpg;
     return p;
@@ -255,8 +256,11 @@ int32_t ensure_reduced_stream(mcdp_plan* plan) {
     const HostPlan& h = plan->host;
     std::vector<EventRec> ev = h.events;
     std::vector<PredRec> pr = h.preds;
-    for (auto& e : ev) e.row = h.slot_of_event[e.event];
     for (auto& q : pr) q.src_row = h.slot_of_event[q.src_event];
+    for (auto& e : ev) {
+        e.row = h.slot_of_event[e.event];
+        if (e.fan_in) e.first_src_row = pr[e.pred_begin].src_row;
+    }
     int32_t rc = upload(plan->d_events_red, ev);
     if (rc) return rc;
     rc = upload(plan->d_preds_red, pr);

@@ -347,7 +347,8 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
         ev.event = uint32_t(e);
         ev.pred_begin = cursor;
         ev.earliest = g.earliest[e];
-        ev.ub = g.earliest[e] + g.max_delay;  // _core.cpp:334
+        ev.first_src_row = 0;
+        ev.pad = 0;
         const int32_t en = entry_of[e];
         uint32_t fan = 0;
         if (en >= 0) {
@@ -370,6 +371,7 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
             }
         }
         ev.fan_in = fan;
+        if (fan) ev.first_src_row = out.preds[cursor].src_row;
         cursor += fan;
         out.max_fan_in = std::max<int32_t>(out.max_fan_in, int32_t(fan));
     }

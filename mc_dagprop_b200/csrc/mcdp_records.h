@@ -14,16 +14,17 @@ constexpr uint32_t kNoDist = 0xFFFFFFFFu;
 constexpr uint32_t kNoAct = 0xFFFFFFFFu;  // precedence entry whose activity index has no duration row
 
 // One event in evaluation order.  `row` is the event's row in the realized/cause arrays
-// (== event id in full/injected mode; a recycled scratch slot in reduced mode).
-// `ub` = earliest + max_delay is rounded once on the host: the same IEEE add the reference
-// performs per sample at _core.cpp:334.
+// (== event id in full/injected mode; a recycled scratch slot in reduced mode).  `first_src_row`
+// repeats the source row of the first precedence entry so that its realized row can be requested
+// as soon as the event record arrives, without waiting for the entry record.
 struct alignas(16) EventRec {
     uint32_t row;
     uint32_t event;
     uint32_t pred_begin;
     uint32_t fan_in;
     double earliest;
-    double ub;
+    uint32_t first_src_row;
+    uint32_t pad;
 };
 static_assert(sizeof(EventRec) == 32, "EventRec must be 32 bytes");
 

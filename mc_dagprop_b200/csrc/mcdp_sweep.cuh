@@ -44,6 +44,7 @@ struct SweepParams {
     uint32_t* hist;
     double thresholds[MCDP_MAX_THRESHOLDS];
     double hist_lo, hist_scale;
+    double max_delay;
     int64_t n, ld;
     int32_t n_levels, n_orphans, n_dists, tab_pool_len;
     int32_t n_thresholds, n_bins, E;
@@ -145,30 +146,26 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
             const int i = i_next;
             i_next = dyn ? grab(par) : i + 1;
             const int4 e0 = __ldg(reinterpret_cast<const int4*>(p.events + i));
-            const double2 e1 = __ldg(reinterpret_cast<const double2*>(p.events + i) + 1);
+            const int4 e1 = __ldg(reinterpret_cast<const int4*>(p.events + i) + 1);
             const uint32_t row = uint32_t(e0.x), fan_in = uint32_t(e0.w);
             const PredRec* pr = p.preds + uint32_t(e0.z);
-            const double earliest = e1.x, ub = e1.y;
+            const double earliest = __hiloint2double(e1.y, e1.x);
+            const double ub = __dadd_rn(earliest, p.max_delay);  // _core.cpp:334
             // _core.cpp:336-337
             double lat_a = earliest, lat_b = earliest;
             int cause_a = -1, cause_b = -1;
-            // rolling prefetch: the next entry's record and predecessor row are requested before the
-            // current entry's delay is drawn, so their latency hides behind the sampling arithmetic
-            int4 nq0 = make_int4(0, 0, 0, 0), nq1 = make_int4(0, 0, 0, 0);
+            // The predecessor row of the NEXT entry is requested before the current entry's delay is
+            // drawn (its source row comes from the event record / a one-word peek at the next entry
+            // record), so the HBM latency of the gather hides behind the sampling arithmetic.
             double2 nrs = make_double2(0.0, 0.0);
-            if (fan_in) {
-                nq0 = __ldg(reinterpret_cast<const int4*>(pr));
-                nq1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
-                nrs = *reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(nq0.x)) * ldb8);
-            }
-            for (uint32_t k = 0; k < fan_in; ++k) {
-                const int4 q0 = nq0, q1 = nq1;
+            if (fan_in) nrs = *reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(e1.z)) * ldb8);
+            for (uint32_t k = 0; k < fan_in; ++k, ++pr) {
+                const int4 q0 = __ldg(reinterpret_cast<const int4*>(pr));
+                const int4 q1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
                 const double2 rs = nrs;
-                ++pr;
                 if (k + 1 < fan_in) {
-                    nq0 = __ldg(reinterpret_cast<const int4*>(pr));
-                    nq1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
-                    nrs = *reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(nq0.x)) * ldb8);
+                    const uint32_t next_row = __ldg(reinterpret_cast<const uint32_t*>(pr + 1));
+                    nrs = *reinterpret_cast<const double2*>(r_lane + size_t(next_row) * ldb8);
                 }
                 const uint32_t act = uint32_t(q0.y);
                 const double base = __hiloint2double(q0.w, q0.z);
