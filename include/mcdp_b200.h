@@ -87,7 +87,7 @@ typedef struct {
 typedef struct {
     int32_t n_thresholds;                  /* 0..4: counts of delay > thresholds[i] */
     double thresholds[MCDP_MAX_THRESHOLDS];
-    int32_t n_bins;                        /* 0 = no histogram, else 1..256 */
+    int32_t n_bins;                        /* 0 = no histogram, else 1..1024 */
     double hist_lo, hist_hi;               /* bin = clamp(floor((delay-lo)/(hi-lo)*n_bins), 0, n_bins-1) */
 } mcdp_stats_desc;
 
@@ -122,6 +122,7 @@ int32_t mcdp_plan_node_count(const mcdp_plan* plan);     /* Simulator::node_coun
 int32_t mcdp_plan_activity_count(const mcdp_plan* plan); /* Simulator::activity_count  _core.cpp:310 */
 int64_t mcdp_plan_pred_count(const mcdp_plan* plan);
 int32_t mcdp_plan_level_count(const mcdp_plan* plan);
+int32_t mcdp_plan_slot_count(const mcdp_plan* plan);     /* realized scratch rows of the reduced mode */
 int32_t mcdp_plan_device(const mcdp_plan* plan);
 /* evaluation order (a topological order; event_evaluation_order_ of _core.cpp:177) and level of each position */
 int32_t mcdp_plan_get_order(const mcdp_plan* plan, int32_t* order_out, int32_t* level_out);

@@ -24,7 +24,7 @@ MAX_THRESHOLDS = 4
 EXPORTED_SYMBOLS = (
     "mcdp_last_error", "mcdp_abi_version", "mcdp_device_count", "mcdp_plan_create", "mcdp_plan_destroy",
     "mcdp_plan_set_option", "mcdp_plan_node_count", "mcdp_plan_activity_count", "mcdp_plan_pred_count",
-    "mcdp_plan_level_count", "mcdp_plan_device", "mcdp_plan_get_order", "mcdp_plan_get_cumulative",
+    "mcdp_plan_level_count", "mcdp_plan_slot_count", "mcdp_plan_device", "mcdp_plan_get_order", "mcdp_plan_get_cumulative",
     "mcdp_run_full_device", "mcdp_run_injected_device", "mcdp_run_reduced_device", "mcdp_transpose_f64_device",
     "mcdp_transpose_i32_device", "mcdp_run_many_host", "mcdp_run_injected_host", "mcdp_run_reduced_host",
     "mcdp_host_alloc", "mcdp_host_free",
@@ -73,7 +73,7 @@ def lib() -> C.CDLL:
         L.mcdp_plan_destroy.argtypes = [vp]
         L.mcdp_plan_destroy.restype = None
         L.mcdp_plan_set_option.argtypes = [vp, i32, i64]
-        for name in ("node_count", "activity_count", "level_count", "device"):
+        for name in ("node_count", "activity_count", "level_count", "slot_count", "device"):
             getattr(L, f"mcdp_plan_{name}").argtypes = [vp]
         L.mcdp_plan_pred_count.argtypes = [vp]
         L.mcdp_plan_pred_count.restype = i64
@@ -197,6 +197,7 @@ class Plan:
         self.A = int(L.mcdp_plan_activity_count(h))
         self.P = int(L.mcdp_plan_pred_count(h))
         self.n_levels = int(L.mcdp_plan_level_count(h))
+        self.n_slots = int(L.mcdp_plan_slot_count(h))
         self.device = int(L.mcdp_plan_device(h))
 
     def close(self):

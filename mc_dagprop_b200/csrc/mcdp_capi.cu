@@ -145,17 +145,25 @@ int32_t upload(DevBuf<T>& buf, const std::vector<T>& v) {
 }
 
 struct LaunchShape {
-    int wpg, gpc, threads;
+    int wpg, gpc, threads, batches;
     unsigned grid;
     size_t smem;
     bool smem_tables;
 };
 
 // How many warps split a level, how many 64-sample groups share a CTA.
-LaunchShape choose_shape(const mcdp_plan* plan, int64_t n) {
+LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false, int n_bins = 0) {
     const HostPlan& h = plan->host;
     LaunchShape s{};
-    const int64_t n_groups = (n + 63) / 64;
+    int64_t n_groups = (n + 63) / 64;
+    int batches = 1;
+    if (reduced) {
+        // once there are more 64-sample batches than warp slots, fold several batches per group so the
+        // global accumulators see one flush per event per group instead of one per 64 samples
+        const int64_t slots = int64_t(plan->sm_count) * 32;
+        batches = int(std::max<int64_t>(1, std::min<int64_t>(64, n_groups / slots)));
+        n_groups = (n_groups + batches - 1) / batches;
+    }
     int wpg = plan->warps_per_group;
     constexpr int kMaxWarps = MCDP_MAX_THREADS / 32;
     int gpc = plan->groups_per_cta;
@@ -186,12 +194,14 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n) {
     gpc = std::max(1, std::min({gpc, 15, kMaxWarps / wpg}));
     s.wpg = wpg;
     s.gpc = gpc;
+    s.batches = batches;
     s.threads = 32 * wpg * gpc;
     s.grid = unsigned((n_groups + gpc - 1) / gpc);
     const size_t need = sizeof(DistRec) * h.dists.size() + sizeof(double) * h.tab_pool.size();
     // keep several CTAs per SM resident: stage only when the tables are a modest share of shared memory
     s.smem_tables = need > 0 && need <= std::min<size_t>(plan->smem_optin, 64 * 1024);
     s.smem = s.smem_tables ? need : 0;
+    if (reduced && n_bins > 0 && batches > 1) s.smem = ((s.smem + 15) & ~size_t(15)) + size_t(wpg * gpc) * size_t(n_bins) * 4;
     return s;
 }
 
@@ -203,7 +213,9 @@ int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p, const LaunchShape& s
         if (s.smem > 48 * 1024) MCDP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s.smem)));
         k<<<s.grid, s.threads, s.smem, stream>>>(p);
     } else {
-        sweep_kernel<MODE, false><<<s.grid, s.threads, 0, stream>>>(p);
+        auto k = sweep_kernel<MODE, false>;
+        if (s.smem > 48 * 1024) MCDP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s.smem)));
+        k<<<s.grid, s.threads, s.smem, stream>>>(p);
     }
     MCDP_CUDA(cudaGetLastError());
     (void)plan;
@@ -229,6 +241,7 @@ SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, 
     p.max_delay = h.max_delay;
     for (int r = 0; r < 10; ++r) p.keys.k[r] = plan->stream_key + uint32_t(r) * 0x9E3779B9u;
     p.warps_per_group = s.wpg;
+    p.batches_per_group = s.batches;
     return p;
 }
 
@@ -374,6 +387,7 @@ int32_t mcdp_plan_node_count(const mcdp_plan* plan) { return plan ? plan->host.E
 int32_t mcdp_plan_activity_count(const mcdp_plan* plan) { return plan ? plan->host.A : 0; }
 int64_t mcdp_plan_pred_count(const mcdp_plan* plan) { return plan ? plan->host.P : 0; }
 int32_t mcdp_plan_level_count(const mcdp_plan* plan) { return plan ? plan->host.n_levels : 0; }
+int32_t mcdp_plan_slot_count(const mcdp_plan* plan) { return plan ? plan->host.n_slots : 0; }
 int32_t mcdp_plan_device(const mcdp_plan* plan) { return plan ? plan->device : -1; }
 
 int32_t mcdp_plan_get_order(const mcdp_plan* plan, int32_t* order_out, int32_t* level_out) {
@@ -445,7 +459,7 @@ int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t
     if (plan->device < 0) return fail(MCDP_ERR_CUDA, "plan was created host-only (MCDP_DEVICE_NONE): there is no CPU execution path");
     if (n < 0) return fail(MCDP_ERR_ARG, "n must be non-negative");
     if (desc->n_thresholds < 0 || desc->n_thresholds > MCDP_MAX_THRESHOLDS) return fail(MCDP_ERR_ARG, "n_thresholds must be 0..4");
-    if (desc->n_bins < 0 || desc->n_bins > 4096) return fail(MCDP_ERR_ARG, "n_bins must be 0..4096");
+    if (desc->n_bins < 0 || desc->n_bins > 1024) return fail(MCDP_ERR_ARG, "n_bins must be 0..1024");
     if (d_hist && desc->n_bins > 0 && !(desc->hist_hi > desc->hist_lo)) return fail(MCDP_ERR_ARG, "hist_hi must exceed hist_lo");
     std::lock_guard<std::mutex> lock(plan->mu);
     DeviceGuard guard(plan->device);
@@ -454,13 +468,18 @@ int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t
     const HostPlan& h = plan->host;
     // scratch rows are recycled slots; samples are processed in chunks that bound the scratch
     const int64_t bytes_per_sample = int64_t(std::max(h.n_slots, 1)) * 8;
-    int64_t chunk = std::max<int64_t>(64, (int64_t(2) << 30) / bytes_per_sample / 64 * 64);
+    // scratch budget: what is already allocated, else half of the free HBM (deep DAGs keep many rows live)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(4) << 30;
+    const int64_t budget = std::max<int64_t>(int64_t(plan->d_scratch.cap) * 8, int64_t(double(free_b) * 0.5));
+    int64_t chunk = std::max<int64_t>(64, budget / bytes_per_sample / 64 * 64);
+    chunk = std::min<int64_t>(chunk, int64_t(1) << 22);
     chunk = std::min<int64_t>(chunk, round_up(std::max<int64_t>(n, 1), 64));
     MCDP_CUDA(plan->d_scratch.ensure(size_t(std::max(h.n_slots, 1)) * size_t(chunk)));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t m = std::min(chunk, n - off);
-        const LaunchShape s = choose_shape(plan, m);
+        const LaunchShape s = choose_shape(plan, m, true, d_hist ? desc->n_bins : 0);
         SweepParams p = base_params(plan, s, m, chunk);
         p.events = plan->d_events_red.p;
         p.preds = plan->d_preds_red.p;

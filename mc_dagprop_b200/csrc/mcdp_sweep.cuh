@@ -51,6 +51,7 @@ struct SweepParams {
     int32_t seed0;
     PhiloxKeys keys;  // round keys of Philox key word 0 (stream_key + r * 0x9E3779B9)
     int32_t warps_per_group;
+    int32_t batches_per_group;  // reduced mode: 64-sample batches folded per group before a flush
 };
 
 __device__ __forceinline__ void group_barrier(int id, int nthreads) {
@@ -71,50 +72,138 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DistRec* dists = p.dists;
     const double* tab = p.tab_pool;
+    size_t smem_used = 0;
     if constexpr (SMEM) {
-        // stage distribution records + inverse-CDF tables + guide tables once per CTA
+        // stage distribution records + guide / inverse-CDF tables once per CTA
         DistRec* s_dists = reinterpret_cast<DistRec*>(smem_raw);
         double* s_tab = reinterpret_cast<double*>(smem_raw + sizeof(DistRec) * p.n_dists);
         const int n16 = int(sizeof(DistRec) / 16) * p.n_dists;
         for (int i = threadIdx.x; i < n16; i += blockDim.x)
             reinterpret_cast<int4*>(s_dists)[i] = __ldg(reinterpret_cast<const int4*>(p.dists) + i);
         for (int i = threadIdx.x; i < p.tab_pool_len; i += blockDim.x) s_tab[i] = __ldg(p.tab_pool + i);
-        __syncthreads();
         dists = s_dists;
         tab = s_tab;
+        smem_used = sizeof(DistRec) * p.n_dists + sizeof(double) * p.tab_pool_len;
     }
-
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    // reduced mode: one private histogram per warp, flushed once per event
+    uint32_t* w_hist = nullptr;
+    if constexpr (MODE == kModeReduced) {
+        if (p.hist && p.batches_per_group > 1) {
+            uint32_t* all = reinterpret_cast<uint32_t*>(smem_raw + ((smem_used + 15) & ~size_t(15)));
+            for (int i = threadIdx.x; i < int(blockDim.x >> 5) * p.n_bins; i += blockDim.x) all[i] = 0u;
+            w_hist = all + warp * p.n_bins;
+        }
+    }
+    if (SMEM || MODE == kModeReduced) __syncthreads();
+
     const int wpg = p.warps_per_group;
     const int group_in_cta = warp / wpg;
     const int wsub = warp - group_in_cta * wpg;
     const int groups_per_cta = (blockDim.x >> 5) / wpg;
-    const int64_t group = int64_t(blockIdx.x) * groups_per_cta + group_in_cta;
-    if (group * 64 >= p.n) return;  // whole group (all its warps) out of range
-    // ld is a multiple of 64, so every lane of a launched group owns two in-bounds columns; columns
-    // >= n are padding (computed and written like the others, never read back by the host side).
-    const int64_t s0 = group * 64 + 2 * lane;
-
-    uint32_t seed_a = 0, seed_b = 1;
-    if constexpr (MODE != kModeInjected) {
-        if (p.seeds) {
-            seed_a = s0 < p.n ? uint32_t(__ldg(p.seeds + s0)) : 0u;
-            seed_b = s0 + 1 < p.n ? uint32_t(__ldg(p.seeds + s0 + 1)) : seed_a + 1u;
-        } else {
-            seed_a = uint32_t(p.seed0) + uint32_t(s0);
-            seed_b = seed_a + 1u;
-        }
-    }
-    const bool paired = ((seed_a & 1u) == 0u) && (seed_b == seed_a + 1u);
+    // A group owns `batches` consecutive 64-sample batches (1 except in reduced mode, where a warp
+    // folds the statistics of all its batches before touching the global accumulators).
+    const int batches = MODE == kModeReduced ? p.batches_per_group : 1;
+    const int64_t batch0 = (int64_t(blockIdx.x) * groups_per_cta + group_in_cta) * batches;
+    if (batch0 * 64 >= p.n) return;  // whole group (all its warps) out of range
     const PhiloxKeys& key0 = p.keys;
-
-    // per-lane column bases; a row is reached with one 32x32->64 multiply-add (ld * 8 < 2^32)
     const uint32_t ldb8 = uint32_t(p.ld) * 8u, ldb4 = uint32_t(p.ld) * 4u;
-    char* const r_lane = reinterpret_cast<char*>(p.realized) + s0 * 8;
-    char* const d_lane = reinterpret_cast<char*>(p.durations) + s0 * 8;
-    const char* const i_lane = reinterpret_cast<const char*>(p.inj) + s0 * 8;
-    char* const c_lane = reinterpret_cast<char*>(p.cause) + s0 * 4;
+
+    // One event for the two samples (columns s0, s0 + 1) a lane owns in one batch.
+    // ld is a multiple of 64, so every lane of a launched batch owns two in-bounds columns; columns
+    // >= n are padding (computed and written like the others, never read back by the host side).
+    // r_lane / d_lane / i_lane / c_lane: per-lane column bases of realized / durations / injected
+    // durations / cause; a row is reached with one 32x32->64 multiply-add (ld * 8 < 2^32).
+    auto event_body = [&](const int4& e0, const int4& e1, char* r_lane, char* d_lane, const char* i_lane, char* c_lane,
+                          uint32_t seed_a, uint32_t seed_b, bool paired, double& ra, double& rb) {
+        const uint32_t row = uint32_t(e0.x), fan_in = uint32_t(e0.w);
+        const PredRec* pr = p.preds + uint32_t(e0.z);
+        const double earliest = __hiloint2double(e1.y, e1.x);
+        const double ub = __dadd_rn(earliest, p.max_delay);  // _core.cpp:334
+        // _core.cpp:336-337
+        double lat_a = earliest, lat_b = earliest;
+        int cause_a = -1, cause_b = -1;
+        // The predecessor row of the NEXT entry is requested before the current entry's delay is
+        // drawn (its source row comes from the event record / a one-word peek at the next entry
+        // record), so the HBM latency of the gather hides behind the sampling arithmetic.
+        double2 nrs = make_double2(0.0, 0.0);
+        if (fan_in) nrs = *reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(e1.z)) * ldb8);
+        for (uint32_t k = 0; k < fan_in; ++k, ++pr) {
+            const int4 q0 = __ldg(reinterpret_cast<const int4*>(pr));
+            const int4 q1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
+            const double2 rs = nrs;
+            if (k + 1 < fan_in) {
+                const uint32_t next_row = __ldg(reinterpret_cast<const uint32_t*>(pr + 1));
+                nrs = *reinterpret_cast<const double2*>(r_lane + size_t(next_row) * ldb8);
+            }
+            const uint32_t act = uint32_t(q0.y);
+            const double base = __hiloint2double(q0.w, q0.z);
+            const uint32_t meta = uint32_t(q1.x);
+            const int src_event = q1.z;
+            double da, db;
+            if constexpr (MODE == kModeInjected) {
+                double2 dd = make_double2(0.0, 0.0);
+                if (act != kNoAct) dd = __ldcs(reinterpret_cast<const double2*>(i_lane + size_t(act) * ldb8));
+                da = dd.x;
+                db = dd.y;
+            } else {
+                if ((meta >> 29) == kKindNone) {
+                    da = db = base;  // _core.cpp:304-305,325
+                } else {
+                    double ea, eb;
+                    sample_extra2<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, seed_a, seed_b, paired,
+                                        key0, ea, eb);
+                    da = __dadd_rn(base, ea);  // _core.cpp:328
+                    db = __dadd_rn(base, eb);
+                }
+                if constexpr (MODE == kModeFull) {
+                    if (act != kNoAct) __stcs(reinterpret_cast<double2*>(d_lane + size_t(act) * ldb8), make_double2(da, db));
+                }
+            }
+            // _core.cpp:341-346
+            const double ta = ref_min(__dadd_rn(rs.x, da), ub);
+            const double tb = ref_min(__dadd_rn(rs.y, db), ub);
+            if (ta >= lat_a) {
+                lat_a = ta;
+                cause_a = src_event;
+            }
+            if (tb >= lat_b) {
+                lat_b = tb;
+                cause_b = src_event;
+            }
+        }
+        // _core.cpp:348-349
+        ra = ref_min(lat_a, ub);
+        rb = ref_min(lat_b, ub);
+        *reinterpret_cast<double2*>(r_lane + size_t(row) * ldb8) = make_double2(ra, rb);
+        if constexpr (MODE != kModeReduced)
+            __stcs(reinterpret_cast<int2*>(c_lane + size_t(row) * ldb4), make_int2(cause_a, cause_b));
+    };
+    auto seeds_of = [&](int64_t s0, uint32_t& seed_a, uint32_t& seed_b, bool& paired) {
+        seed_a = 0u;
+        seed_b = 1u;
+        if constexpr (MODE != kModeInjected) {
+            if (p.seeds) {
+                seed_a = s0 < p.n ? uint32_t(__ldg(p.seeds + s0)) : 0u;
+                seed_b = s0 + 1 < p.n ? uint32_t(__ldg(p.seeds + s0 + 1)) : seed_a + 1u;
+            } else {
+                seed_a = uint32_t(p.seed0) + uint32_t(s0);
+                seed_b = seed_a + 1u;
+            }
+        }
+        paired = ((seed_a & 1u) == 0u) && (seed_b == seed_a + 1u);
+    };
+
+    // full / injected mode: the lane's two columns and seeds are fixed for the whole sweep
+    const int64_t s0_fixed = batch0 * 64 + 2 * lane;
+    uint32_t seed_a0, seed_b0;
+    bool paired0;
+    seeds_of(s0_fixed, seed_a0, seed_b0, paired0);
+    char* const r_lane0 = reinterpret_cast<char*>(p.realized) + s0_fixed * 8;
+    char* const d_lane0 = reinterpret_cast<char*>(p.durations) + s0_fixed * 8;
+    const char* const i_lane0 = reinterpret_cast<const char*>(p.inj) + s0_fixed * 8;
+    char* const c_lane0 = reinterpret_cast<char*>(p.cause) + s0_fixed * 4;
 
     // Level scheduling.  One warp per group: events in stream order, no synchronisation.  Several
     // warps per group: the warps of a group pull event positions from a shared-memory counter (one
@@ -147,102 +236,78 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
             i_next = dyn ? grab(par) : i + 1;
             const int4 e0 = __ldg(reinterpret_cast<const int4*>(p.events + i));
             const int4 e1 = __ldg(reinterpret_cast<const int4*>(p.events + i) + 1);
-            const uint32_t row = uint32_t(e0.x), fan_in = uint32_t(e0.w);
-            const PredRec* pr = p.preds + uint32_t(e0.z);
-            const double earliest = __hiloint2double(e1.y, e1.x);
-            const double ub = __dadd_rn(earliest, p.max_delay);  // _core.cpp:334
-            // _core.cpp:336-337
-            double lat_a = earliest, lat_b = earliest;
-            int cause_a = -1, cause_b = -1;
-            // The predecessor row of the NEXT entry is requested before the current entry's delay is
-            // drawn (its source row comes from the event record / a one-word peek at the next entry
-            // record), so the HBM latency of the gather hides behind the sampling arithmetic.
-            double2 nrs = make_double2(0.0, 0.0);
-            if (fan_in) nrs = *reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(e1.z)) * ldb8);
-            for (uint32_t k = 0; k < fan_in; ++k, ++pr) {
-                const int4 q0 = __ldg(reinterpret_cast<const int4*>(pr));
-                const int4 q1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
-                const double2 rs = nrs;
-                if (k + 1 < fan_in) {
-                    const uint32_t next_row = __ldg(reinterpret_cast<const uint32_t*>(pr + 1));
-                    nrs = *reinterpret_cast<const double2*>(r_lane + size_t(next_row) * ldb8);
-                }
-                const uint32_t act = uint32_t(q0.y);
-                const double base = __hiloint2double(q0.w, q0.z);
-                const uint32_t meta = uint32_t(q1.x);
-                const int src_event = q1.z;
-                double da, db;
-                if constexpr (MODE == kModeInjected) {
-                    double2 dd = make_double2(0.0, 0.0);
-                    if (act != kNoAct) dd = __ldcs(reinterpret_cast<const double2*>(i_lane + size_t(act) * ldb8));
-                    da = dd.x;
-                    db = dd.y;
-                } else {
-                    if ((meta >> 29) == kKindNone) {
-                        da = db = base;  // _core.cpp:304-305,325
-                    } else {
-                        double ea, eb;
-                        sample_extra2<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, seed_a, seed_b,
-                                            paired, key0, ea, eb);
-                        da = __dadd_rn(base, ea);  // _core.cpp:328
-                        db = __dadd_rn(base, eb);
-                    }
-                    if constexpr (MODE == kModeFull) {
-                        if (act != kNoAct)
-                            __stcs(reinterpret_cast<double2*>(d_lane + size_t(act) * ldb8), make_double2(da, db));
-                    }
-                }
-                // _core.cpp:341-346
-                const double ta = ref_min(__dadd_rn(rs.x, da), ub);
-                const double tb = ref_min(__dadd_rn(rs.y, db), ub);
-                if (ta >= lat_a) {
-                    lat_a = ta;
-                    cause_a = src_event;
-                }
-                if (tb >= lat_b) {
-                    lat_b = tb;
-                    cause_b = src_event;
-                }
-            }
-            // _core.cpp:348-349
-            const double ra = ref_min(lat_a, ub), rb = ref_min(lat_b, ub);
-            *reinterpret_cast<double2*>(r_lane + size_t(row) * ldb8) = make_double2(ra, rb);
-            if constexpr (MODE != kModeReduced)
-                __stcs(reinterpret_cast<int2*>(c_lane + size_t(row) * ldb4), make_int2(cause_a, cause_b));
-            if constexpr (MODE == kModeReduced) {
-                const bool valid_a = s0 < p.n, valid_b = s0 + 1 < p.n;
+            if constexpr (MODE != kModeReduced) {
+                double ra, rb;
+                event_body(e0, e1, r_lane0, d_lane0, i_lane0, c_lane0, seed_a0, seed_b0, paired0, ra, rb);
+            } else {
+                // fold the delay statistics of all batches of this group, then one flush per event
+                const double earliest = __hiloint2double(e1.y, e1.x);
                 const uint32_t ev = uint32_t(e0.y);
-                const double xa = valid_a ? ra - earliest : 0.0;
-                const double xb = valid_b ? rb - earliest : 0.0;
+                double acc = 0.0, acc2 = 0.0;
+                int late[MCDP_MAX_THRESHOLDS] = {0, 0, 0, 0};
+                for (int b = 0; b < batches; ++b) {
+                    const int64_t s0 = (batch0 + b) * 64 + 2 * lane;
+                    if ((batch0 + b) * 64 >= p.n) break;  // warp-uniform
+                    uint32_t seed_a, seed_b;
+                    bool paired;
+                    seeds_of(s0, seed_a, seed_b, paired);
+                    double ra, rb;
+                    event_body(e0, e1, reinterpret_cast<char*>(p.realized) + s0 * 8, nullptr, nullptr, nullptr, seed_a, seed_b,
+                               paired, ra, rb);
+                    const bool valid_a = s0 < p.n, valid_b = s0 + 1 < p.n;
+                    const double xa = valid_a ? ra - earliest : 0.0;
+                    const double xb = valid_b ? rb - earliest : 0.0;
+                    acc += xa + xb;
+                    acc2 += xa * xa + xb * xb;
+#pragma unroll
+                    for (int t = 0; t < MCDP_MAX_THRESHOLDS; ++t)
+                        if (t < p.n_thresholds) late[t] += int(valid_a && xa > p.thresholds[t]) + int(valid_b && xb > p.thresholds[t]);
+                    if (p.hist) {
+                        const int nb = p.n_bins;
+                        int ba = min(max(int(floor((xa - p.hist_lo) * p.hist_scale)), 0), nb - 1);
+                        int bb = min(max(int(floor((xb - p.hist_lo) * p.hist_scale)), 0), nb - 1);
+                        if (w_hist) {  // several batches per group: private shared-memory histogram
+                            if (valid_a) atomicAdd(w_hist + ba, 1u);
+                            if (valid_b) atomicAdd(w_hist + bb, 1u);
+                        } else {  // single batch: aggregate equal bins across the warp, one atomic per distinct bin
+                            if (!valid_a) ba = -1 - lane;  // unique keys: match groups of size 1, skipped below
+                            if (!valid_b) bb = -1 - lane;
+                            uint32_t* h = p.hist + size_t(ev) * nb;
+                            const unsigned ga = __match_any_sync(0xFFFFFFFFu, ba);
+                            if (ba >= 0 && lane == __ffs(ga) - 1) atomicAdd(h + ba, uint32_t(__popc(ga)));
+                            const unsigned gb = __match_any_sync(0xFFFFFFFFu, bb);
+                            if (bb >= 0 && lane == __ffs(gb) - 1) atomicAdd(h + bb, uint32_t(__popc(gb)));
+                        }
+                    }
+                }
                 if (p.sum) {
-                    const double s = warp_sum(xa + xb);
+                    const double s = warp_sum(acc);
                     if (lane == 0) atomicAdd(p.sum + ev, s);
                 }
                 if (p.sumsq) {
-                    const double s = warp_sum(xa * xa + xb * xb);
+                    const double s = warp_sum(acc2);
                     if (lane == 0) atomicAdd(p.sumsq + ev, s);
                 }
                 if (p.late) {
-                    for (int t = 0; t < p.n_thresholds; ++t) {
-                        const unsigned ma = __ballot_sync(0xFFFFFFFFu, valid_a && xa > p.thresholds[t]);
-                        const unsigned mb = __ballot_sync(0xFFFFFFFFu, valid_b && xb > p.thresholds[t]);
-                        const int c = __popc(ma) + __popc(mb);
-                        if (lane == 0 && c) atomicAdd(p.late + size_t(t) * p.E + ev, (unsigned long long)c);
+#pragma unroll
+                    for (int t = 0; t < MCDP_MAX_THRESHOLDS; ++t) {
+                        if (t < p.n_thresholds) {
+                            const int c = __reduce_add_sync(0xFFFFFFFFu, late[t]);
+                            if (lane == 0 && c) atomicAdd(p.late + size_t(t) * p.E + ev, (unsigned long long)c);
+                        }
                     }
                 }
-                if (p.hist) {
-                    const int nb = p.n_bins;
-                    int ba = int(floor((xa - p.hist_lo) * p.hist_scale));
-                    int bb = int(floor((xb - p.hist_lo) * p.hist_scale));
-                    ba = min(max(ba, 0), nb - 1);
-                    bb = min(max(bb, 0), nb - 1);
-                    if (!valid_a) ba = -1 - lane;  // unique keys: match groups of size 1, skipped below
-                    if (!valid_b) bb = -1 - lane;
-                    uint32_t* h = p.hist + size_t(ev) * nb;
-                    const unsigned ga = __match_any_sync(0xFFFFFFFFu, ba);
-                    if (ba >= 0 && lane == __ffs(ga) - 1) atomicAdd(h + ba, uint32_t(__popc(ga)));
-                    const unsigned gb = __match_any_sync(0xFFFFFFFFu, bb);
-                    if (bb >= 0 && lane == __ffs(gb) - 1) atomicAdd(h + bb, uint32_t(__popc(gb)));
+                if (w_hist) {
+                    __syncwarp();
+                    uint32_t* h = p.hist + size_t(ev) * p.n_bins;
+                    for (int b = lane; b < p.n_bins; b += 32) {
+                        const uint32_t v = w_hist[b];
+                        if (v) {
+                            atomicAdd(h + b, v);
+                            w_hist[b] = 0u;
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -251,6 +316,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
 
     if constexpr (MODE == kModeFull) {
         // activities no precedence entry references still get their sampled duration (_core.cpp:323-329)
+        char* const d_lane = d_lane0;
         for (int i = wsub; i < p.n_orphans; i += wpg) {
             const int4 q0 = __ldg(reinterpret_cast<const int4*>(p.orphans + i));
             const int4 q1 = __ldg(reinterpret_cast<const int4*>(p.orphans + i) + 1);
@@ -259,7 +325,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
             double da = base, db = base;
             if ((meta >> 29) != kKindNone) {
                 double ea, eb;
-                sample_extra2<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, seed_a, seed_b, paired,
+                sample_extra2<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, seed_a0, seed_b0, paired0,
                                     key0, ea, eb);
                 da = __dadd_rn(base, ea);
                 db = __dadd_rn(base, eb);
