@@ -238,6 +238,7 @@ SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, 
     p.n_dists = int32_t(h.dists.size());
     p.tab_pool_len = int32_t(h.tab_pool.size());
     p.E = h.E;
+    p.last_pred = h.P > 0 ? uint32_t(h.P - 1) : 0u;
     p.max_delay = h.max_delay;
     for (int r = 0; r < 10; ++r) p.keys.k[r] = plan->stream_key + uint32_t(r) * 0x9E3779B9u;
     p.warps_per_group = s.wpg;

@@ -93,7 +93,7 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                 // [j/G, (j+1)/G) holds more than one cumulative boundary -- then the guide entry plus one
                 // compare-and-step IS the lower bound and the device skips the scan loop.  Tables that
                 // do not reach that within the cap keep the loop (flags bit2 / meta scan bit).
-                int g = 0;
+                int g = 1;  // >= 1 so that the device's `hi >> (32 - g)` is always a valid shift
                 bool scan = false;
                 if (n >= 2) {
                     double sum0 = 0.0;
@@ -134,7 +134,7 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                     // std::discrete_distribution with < 2 weights always returns index 0
                     // (libstdc++ random.tcc:2660-2664,2703-2704).
                     cp[0] = 1.0;
-                    guide[0] = 0;
+                    guide[0] = guide[1] = 0;
                     break;
                 }
                 // libstdc++ random.tcc:2655-2678: normalise, partial sums, last = 1 -- same
@@ -332,7 +332,13 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
         const bool table = r.kind == MCDP_DIST_EMP_ABS || r.kind == MCDP_DIST_EMP_REL;
         pr.meta = pack_meta(uint32_t(r.kind), table ? uint32_t(r.guide_log2) : 0u, table ? uint32_t(r.tab_len) : 0u,
                             (r.flags & 4) ? 1u : 0u);
-        pr.tab_off = table ? uint32_t(r.tab_off) : 0u;
+        if (table) {
+            // byte offsets into the pool: guide block, and the cumulative array right behind it
+            pr.tab_off = uint32_t(r.tab_off) * 8u;
+            pr.dist = (uint32_t(r.tab_off) + guide_doubles(uint32_t(r.guide_log2))) * 8u;
+        } else {
+            pr.tab_off = 0u;
+        }
     };
 
     // the stream

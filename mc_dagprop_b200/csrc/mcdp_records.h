@@ -33,7 +33,8 @@ static_assert(sizeof(EventRec) == 32, "EventRec must be 32 bytes");
 // table lookup do not wait on a dependent DistRec load.
 //   meta = kind << 29 | guide_log2 << 24 | scan << 23 | table_len      (kind 7 = no distribution;
 //          scan = 1 when a guide bucket may hold more than one cumulative boundary)
-//   tab_off: table block in the pool, in 8-byte units: [guide: 2^g u32][cp: len f64][values: len f64]
+//   table block in the pool: [guide: 2^g u32][cp: len f64][values: len f64]; for table kinds
+//   `tab_off` is the BYTE offset of the guide and `dist` the BYTE offset of cp (values follow cp)
 struct alignas(16) PredRec {
     uint32_t src_row;
     uint32_t act;
@@ -41,7 +42,7 @@ struct alignas(16) PredRec {
     uint32_t meta;
     uint32_t tab_off;
     uint32_t src_event; // value written to cause_event
-    uint32_t dist;      // index into DistRec[] (parameters of constant / exponential / gamma), kNoDist = none
+    uint32_t dist;      // index into DistRec[] (constant / exponential / gamma), byte offset of cp (tables), kNoDist = none
 };
 static_assert(sizeof(PredRec) == 32, "PredRec must be 32 bytes");
 

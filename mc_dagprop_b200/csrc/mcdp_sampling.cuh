@@ -83,16 +83,16 @@ __device__ __forceinline__ uint32_t guide_ld(const uint32_t* p) {
 // random.tcc:2709-2713): the guide table (four buckets per entry) gives the first candidate, one
 // unconditional compare-and-step follows, and a scan loop that almost never iterates finishes.
 template <bool SMEM>
-__device__ __forceinline__ int emp_index(const uint32_t* guide, const double* cp, uint32_t g, bool scan, uint32_t hi,
-                                         double u) {
-    // floor(u * 2^g) == (X >> 12) >> (52 - g) == hi >> (32 - g)
-    const uint32_t j = g ? (hi >> (32u - g)) : 0u;
-    int idx = static_cast<int>(guide_ld<SMEM>(guide + j));
-    idx += tab_ld<SMEM>(cp + idx) < u;  // cp[len-1] == 1.0 > u: never steps past the end
-    if (scan) {                         // only tables whose guide buckets may hold several boundaries
-        while (tab_ld<SMEM>(cp + idx) < u) ++idx;
+__device__ __forceinline__ double emp_value(const char* guide_b, const char* cp_b, uint32_t g, uint32_t len8, bool scan,
+                                            uint32_t hi, double u) {
+    // floor(u * 2^g) == (X >> 12) >> (52 - g) == hi >> (32 - g),  1 <= g <= 20
+    const uint32_t j = hi >> (32u - g);
+    uint32_t off = guide_ld<SMEM>(reinterpret_cast<const uint32_t*>(guide_b) + j) * 8u;
+    if (tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off)) < u) off += 8u;  // cp[len-1] == 1.0 > u: stays in range
+    if (scan) {  // only tables whose guide buckets may hold several boundaries
+        while (tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off)) < u) off += 8u;
     }
-    return idx;
+    return tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off + len8));
 }
 
 // (k + 1/2) * 2^-23 for the top 23 bits k of w: an fp32 uniform strictly inside (0,1), exact.
@@ -185,19 +185,20 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, c
     }
     // one 64-bit draw per sample
     uint32_t lo_a, hi_a, lo_b, hi_b;
-    {
+    if (paired) {  // seeds {2k, 2k+1}: one block, words 0-1 / 2-3
         const Philox4 r = philox4x32_10(seed_a >> 1, act, 0u, kTagPair, key0);
-        const bool odd = seed_a & 1u;
-        lo_a = odd ? r.z : r.x;
-        hi_a = odd ? r.w : r.y;
+        lo_a = r.x;
+        hi_a = r.y;
         lo_b = r.z;
         hi_b = r.w;
-    }
-    if (!paired) {
-        const Philox4 r = philox4x32_10(seed_b >> 1, act, 0u, kTagPair, key0);
-        const bool odd = seed_b & 1u;
-        lo_b = odd ? r.z : r.x;
-        hi_b = odd ? r.w : r.y;
+    } else {
+        const Philox4 ra = philox4x32_10(seed_a >> 1, act, 0u, kTagPair, key0);
+        const Philox4 rb = philox4x32_10(seed_b >> 1, act, 0u, kTagPair, key0);
+        const bool odd_a = seed_a & 1u, odd_b = seed_b & 1u;
+        lo_a = odd_a ? ra.z : ra.x;
+        hi_a = odd_a ? ra.w : ra.y;
+        lo_b = odd_b ? rb.z : rb.x;
+        hi_b = odd_b ? rb.w : rb.y;
     }
     const double ua = uniform52(lo_a, hi_a), ub = uniform52(lo_b, hi_b);
     if (kind == MCDP_DIST_EXPONENTIAL) {
@@ -214,17 +215,14 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, c
         eb = __dmul_rn(xb, base);
         return;
     }
-    // empirical tables: pool block = [guide u32 x 2^g][cp f64 x len][values f64 x len]
-    const uint32_t g = (meta >> 24) & 31u, len = meta & 0x7FFFFFu;
+    // empirical tables: pool block = [guide u32 x 2^g][cp f64 x len][values f64 x len]; the record
+    // carries the byte offsets of guide (tab_off) and cp (dist)
+    const uint32_t g = (meta >> 24) & 31u, len8 = (meta & 0x7FFFFFu) * 8u;
     const bool scan = meta & 0x800000u;
-    const double* blk = tab + tab_off;
-    const uint32_t* guide = reinterpret_cast<const uint32_t*>(blk);
-    const double* cp = blk + guide_doubles(g);
-    const double* vals = cp + len;
-    const int ia = emp_index<SMEM>(guide, cp, g, scan, hi_a, ua);
-    const int ib = emp_index<SMEM>(guide, cp, g, scan, hi_b, ub);
-    const double va = tab_ld<SMEM>(vals + ia);
-    const double vb = tab_ld<SMEM>(vals + ib);
+    const char* guide_b = reinterpret_cast<const char*>(tab) + tab_off;
+    const char* cp_b = reinterpret_cast<const char*>(tab) + dist;
+    const double va = emp_value<SMEM>(guide_b, cp_b, g, len8, scan, hi_a, ua);
+    const double vb = emp_value<SMEM>(guide_b, cp_b, g, len8, scan, hi_b, ub);
     if (kind == MCDP_DIST_EMP_ABS) {  // _core.cpp:125
         ea = va;
         eb = vb;

@@ -48,6 +48,7 @@ struct SweepParams {
     int64_t n, ld;
     int32_t n_levels, n_orphans, n_dists, tab_pool_len;
     int32_t n_thresholds, n_bins, E;
+    uint32_t last_pred;  // index of the last precedence record (prefetch clamp)
     int32_t seed0;
     PhiloxKeys keys;  // round keys of Philox key word 0 (stream_key + r * 0x9E3779B9)
     int32_t warps_per_group;
@@ -57,6 +58,8 @@ struct SweepParams {
 __device__ __forceinline__ void group_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -236,6 +239,12 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
             i_next = dyn ? grab(par) : i + 1;
             const int4 e0 = __ldg(reinterpret_cast<const int4*>(p.events + i));
             const int4 e1 = __ldg(reinterpret_cast<const int4*>(p.events + i) + 1);
+            if (dyn) {
+                // the warps of a group walk the level's records front to back: pull the lines a sibling
+                // warp will need about one round from now into this SM's L1
+                prefetch_l1(p.events + min(i + wpg, p.E - 1));
+                prefetch_l1(p.preds + min(uint32_t(e0.z) + 4u * uint32_t(wpg), p.last_pred));
+            }
             if constexpr (MODE != kModeReduced) {
                 double ra, rb;
                 event_body(e0, e1, r_lane0, d_lane0, i_lane0, c_lane0, seed_a0, seed_b0, paired0, ra, rb);
