@@ -270,10 +270,12 @@ int32_t ensure_reduced_stream(mcdp_plan* plan) {
     const HostPlan& h = plan->host;
     std::vector<EventRec> ev = h.events;
     std::vector<PredRec> pr = h.preds;
-    for (auto& q : pr) q.src_row = h.slot_of_event[q.src_event];
+    for (auto& q : pr) q.src_row = h.slot_of_event[q.src_row];  // host stream rows are event ids
     for (auto& e : ev) {
         e.row = h.slot_of_event[e.event];
         if (e.fan_in) e.first_src_row = pr[e.pred_begin].src_row;
+        for (uint32_t k = 0; k < e.fan_in; ++k)
+            pr[e.pred_begin + k].next_src_row = k + 1 < e.fan_in ? pr[e.pred_begin + k + 1].src_row : 0u;
     }
     int32_t rc = upload(plan->d_events_red, ev);
     if (rc) return rc;

@@ -361,7 +361,7 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
             for (int64_t k = g.prec_off[en]; k < g.prec_off[en + 1]; ++k, ++fan) {
                 PredRec& pr = out.preds[cursor + fan];
                 pr.src_row = uint32_t(g.pred_src[k]);
-                pr.src_event = uint32_t(g.pred_src[k]);
+                pr.next_src_row = k + 1 < g.prec_off[en + 1] ? uint32_t(g.pred_src[k + 1]) : 0u;
                 pr.meta = pack_meta(kKindNone, 0, 0);
                 pr.tab_off = 0;
                 pr.dist = kNoDist;

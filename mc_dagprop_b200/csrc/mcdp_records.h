@@ -36,12 +36,12 @@ static_assert(sizeof(EventRec) == 32, "EventRec must be 32 bytes");
 //   table block in the pool: [guide: 2^g u32][cp: len f64][values: len f64]; for table kinds
 //   `tab_off` is the BYTE offset of the guide and `dist` the BYTE offset of cp (values follow cp)
 struct alignas(16) PredRec {
-    uint32_t src_row;
+    uint32_t src_row;   // row of the source event's realized time; in full/injected mode also the value of cause_event
     uint32_t act;
     double base;        // Activity.minimal_duration
     uint32_t meta;
     uint32_t tab_off;
-    uint32_t src_event; // value written to cause_event
+    uint32_t next_src_row; // src_row of the FOLLOWING entry of the same event (gather prefetch), else 0
     uint32_t dist;      // index into DistRec[] (constant / exponential / gamma), byte offset of cp (tables), kNoDist = none
 };
 static_assert(sizeof(PredRec) == 32, "PredRec must be 32 bytes");

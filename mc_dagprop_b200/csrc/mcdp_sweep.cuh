@@ -128,22 +128,19 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
         double lat_a = earliest, lat_b = earliest;
         int cause_a = -1, cause_b = -1;
         // The predecessor row of the NEXT entry is requested before the current entry's delay is
-        // drawn (its source row comes from the event record / a one-word peek at the next entry
-        // record), so the HBM latency of the gather hides behind the sampling arithmetic.
+        // drawn (its source row is carried by the event record / the current entry record), so the
+        // HBM latency of the gather hides behind the sampling arithmetic.
         double2 nrs = make_double2(0.0, 0.0);
         if (fan_in) nrs = *reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(e1.z)) * ldb8);
         for (uint32_t k = 0; k < fan_in; ++k, ++pr) {
             const int4 q0 = __ldg(reinterpret_cast<const int4*>(pr));
             const int4 q1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
             const double2 rs = nrs;
-            if (k + 1 < fan_in) {
-                const uint32_t next_row = __ldg(reinterpret_cast<const uint32_t*>(pr + 1));
-                nrs = *reinterpret_cast<const double2*>(r_lane + size_t(next_row) * ldb8);
-            }
+            if (k + 1 < fan_in) nrs = *reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(q1.z)) * ldb8);
             const uint32_t act = uint32_t(q0.y);
             const double base = __hiloint2double(q0.w, q0.z);
             const uint32_t meta = uint32_t(q1.x);
-            const int src_event = q1.z;
+            const int src_event = q0.x;  // full / injected mode: rows are event ids
             double da, db;
             if constexpr (MODE == kModeInjected) {
                 double2 dd = make_double2(0.0, 0.0);
