@@ -103,7 +103,10 @@ enum {
     MCDP_OPT_STREAM_KEY = 0,    /* uint32 Philox key word 0 (default 0) */
     MCDP_OPT_WARPS_PER_GROUP = 1, /* warps that share one 64-sample group and split each topological level; 0 = auto */
     MCDP_OPT_GROUPS_PER_CTA = 2,  /* 64-sample groups per CTA; 0 = auto */
-    MCDP_OPT_HOST_CHUNK = 3       /* samples per device chunk in the *_host calls; 0 = auto from free HBM */
+    MCDP_OPT_HOST_CHUNK = 3,      /* samples per device chunk in the *_host calls; 0 = auto from free HBM */
+    MCDP_OPT_RNG_STREAM = 4       /* 0 = Philox contract (default); 1 = reference-compatible stream: Xoshiro256++
+                                     in activity-index order with the libstdc++ transforms (_core.cpp:313-329),
+                                     full-output calls only, at most 64 distributions */
 };
 
 const char* mcdp_last_error(void);

@@ -17,7 +17,8 @@ LIB_PATH = os.path.join(_PKG, "libmcdp_b200.so")
 
 MCDP_OK, MCDP_ERR_INVALID, MCDP_ERR_CUDA, MCDP_ERR_ARG = 0, 1, 2, 3
 DEVICE_NONE = -1
-OPT_STREAM_KEY, OPT_WARPS_PER_GROUP, OPT_GROUPS_PER_CTA, OPT_HOST_CHUNK = 0, 1, 2, 3
+OPT_STREAM_KEY, OPT_WARPS_PER_GROUP, OPT_GROUPS_PER_CTA, OPT_HOST_CHUNK, OPT_RNG_STREAM = 0, 1, 2, 3, 4
+RNG_PHILOX, RNG_REFERENCE = 0, 1
 MAX_THRESHOLDS = 4
 
 #: every symbol include/mcdp_b200.h declares (tests check the library exports all of them)

@@ -12,6 +12,7 @@
 
 #include "../../include/mcdp_b200.h"
 #include "mcdp_plan.hpp"
+#include "mcdp_compat.cuh"
 #include "mcdp_sweep.cuh"
 
 using namespace mcdp;
@@ -110,6 +111,9 @@ struct mcdp_plan {
     uint32_t stream_key = 0;
     int warps_per_group = 0, groups_per_cta = 0;
     int64_t host_chunk = 0;
+    int rng_stream = 0;  // 0 Philox contract, 1 reference-compatible Xoshiro stream
+    DevBuf<ActRec> d_acts;
+    DevBuf<double> d_norm_cache;
     // host-call workspaces
     HostSlot slots[2];
     DevBuf<double> d_stat_f64;
@@ -129,6 +133,8 @@ struct mcdp_plan {
         d_events_red.release();
         d_preds_red.release();
         d_scratch.release();
+        d_acts.release();
+        d_norm_cache.release();
         d_stat_f64.release();
         d_stat_u64.release();
         d_stat_u32.release();
@@ -287,6 +293,37 @@ int32_t ensure_reduced_stream(mcdp_plan* plan) {
 
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// reference-compatible stream: draw durations[A][ld] with the Xoshiro sampler; the caller then
+// sweeps them in duration-injection mode
+int32_t launch_compat_sampler(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n, double* d_durations,
+                              int64_t ld, cudaStream_t stream) {
+    const HostPlan& h = plan->host;
+    if (h.A == 0 || n <= 0) return MCDP_OK;
+    if (plan->d_acts.cap < size_t(h.A)) {
+        std::vector<ActRec> acts(static_cast<size_t>(h.A));
+        for (int32_t a = 0; a < h.A; ++a) acts[a] = ActRec{h.act_base[a], h.act_dist[a], 0u};
+        int32_t rc = upload(plan->d_acts, acts);
+        if (rc) return rc;
+    }
+    MCDP_CUDA(plan->d_norm_cache.ensure(std::max<size_t>(h.dists.size(), 1) * size_t(ld)));
+    CompatParams cp{};
+    cp.acts = plan->d_acts.p;
+    cp.dists = plan->d_dists.p;
+    cp.tab_pool = plan->d_tab.p;
+    cp.seeds = d_seeds;
+    cp.durations = d_durations;
+    cp.norm_cache = plan->d_norm_cache.p;
+    cp.n = n;
+    cp.ld = ld;
+    cp.A = h.A;
+    cp.n_dists = int32_t(h.dists.size());
+    cp.seed0 = seed0;
+    const int64_t cols = round_up(n, 64);
+    compat_sample_kernel<<<unsigned((cols + 127) / 128), 128, 0, stream>>>(cp);
+    MCDP_CUDA(cudaGetLastError());
+    return MCDP_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -377,6 +414,12 @@ int32_t mcdp_plan_set_option(mcdp_plan* plan, int32_t option, int64_t value) {
             if (value < 0 || value > 15) return fail(MCDP_ERR_ARG, "groups per CTA must be 0..15");
             plan->groups_per_cta = int(value);
             break;
+        case MCDP_OPT_RNG_STREAM:
+            if (value != 0 && value != 1) return fail(MCDP_ERR_ARG, "rng stream must be 0 (Philox) or 1 (reference-compatible)");
+            if (value == 1 && plan->host.dists.size() > 64)
+                return fail(MCDP_ERR_ARG, "the reference-compatible stream supports at most 64 distributions");
+            plan->rng_stream = int(value);
+            break;
         case MCDP_OPT_HOST_CHUNK:
             if (value < 0) return fail(MCDP_ERR_ARG, "host chunk must be non-negative");
             plan->host_chunk = value;
@@ -433,6 +476,13 @@ int32_t mcdp_run_full_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t se
     p.realized = d_realized;
     p.durations = d_durations;
     p.cause = d_cause;
+    if (plan->rng_stream == 1) {
+        std::lock_guard<std::mutex> lock(plan->mu);
+        rc = launch_compat_sampler(plan, d_seeds, seed0, n, d_durations, ld, static_cast<cudaStream_t>(stream));
+        if (rc) return rc;
+        p.inj = d_durations;
+        return launch_sweep<kModeInjected>(plan, p, s, static_cast<cudaStream_t>(stream));
+    }
     return launch_sweep<kModeFull>(plan, p, s, static_cast<cudaStream_t>(stream));
 }
 
@@ -461,6 +511,7 @@ int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t
     if (!plan || !desc) return fail(MCDP_ERR_ARG, "null argument");
     if (plan->device < 0) return fail(MCDP_ERR_CUDA, "plan was created host-only (MCDP_DEVICE_NONE): there is no CPU execution path");
     if (n < 0) return fail(MCDP_ERR_ARG, "n must be non-negative");
+    if (plan->rng_stream == 1) return fail(MCDP_ERR_ARG, "the reference-compatible stream is available for full-output calls only");
     if (desc->n_thresholds < 0 || desc->n_thresholds > MCDP_MAX_THRESHOLDS) return fail(MCDP_ERR_ARG, "n_thresholds must be 0..4");
     if (desc->n_bins < 0 || desc->n_bins > 1024) return fail(MCDP_ERR_ARG, "n_bins must be 0..1024");
     if (d_hist && desc->n_bins > 0 && !(desc->hist_hi > desc->hist_lo)) return fail(MCDP_ERR_ARG, "hist_hi must exceed hist_lo");
@@ -558,7 +609,17 @@ int32_t mcdp_run_many_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, dou
         p.realized = sl.realized.p;
         p.durations = sl.durations.p;
         p.cause = sl.cause.p;
-        rc = launch_sweep<kModeFull>(plan, p, s, sl.stream);
+        if (plan->rng_stream == 1) {
+            // the sampler's normal cache is plan-wide scratch: chunks of the compatible stream run one after another
+            for (auto& other : plan->slots)
+                if (other.stream && other.stream != sl.stream) MCDP_CUDA(cudaStreamSynchronize(other.stream));
+            rc = launch_compat_sampler(plan, sl.seeds.p, 0, m, sl.durations.p, chunk, sl.stream);
+            if (rc) break;
+            p.inj = sl.durations.p;
+            rc = launch_sweep<kModeInjected>(plan, p, s, sl.stream);
+        } else {
+            rc = launch_sweep<kModeFull>(plan, p, s, sl.stream);
+        }
         if (rc) break;
         if (realized && E) {
             MCDP_CUDA(sl.t_realized.ensure(size_t(E) * size_t(chunk)));

@@ -52,6 +52,7 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                 r.p[1] = p1;
                 r.p[2] = std::isinf(p1) ? 1.0 : -std::expm1(-p1 / p0);  // P(x <= max_scale)
                 if (r.p[2] < 0x1p-10) r.flags |= 2;
+                r.p[7] = 1.0 / p0;  // rate, as ExponentialDist's constructor computes it (_core.cpp:81)
                 break;
             }
             case MCDP_DIST_GAMMA: {
@@ -221,6 +222,9 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
         auto it = type_to_dist.find(g.act_type[i]);
         act_dist[a] = it == type_to_dist.end() ? kNoDist : uint32_t(it->second);
     }
+
+    out.act_base = base;
+    out.act_dist = act_dist;
 
     // precedence: the last entry for a target wins (preds_by_target[tgt] = entry.second, _core.cpp:240);
     // indices are bounds-checked here -- the reference does not (undefined behaviour there).

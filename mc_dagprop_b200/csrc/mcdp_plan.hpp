@@ -29,6 +29,10 @@ struct HostPlan {
     std::vector<int32_t> dist_types;   // activity_type of dists[i]
     std::vector<double> tab_pool;      // [guide u32 x 2^g][cp][values] blocks
 
+    // per-activity view in index order (reference-stream compatibility sampler)
+    std::vector<double> act_base;
+    std::vector<uint32_t> act_dist;
+
     // introspection
     std::vector<int32_t> order;        // event id at each position
     std::vector<int32_t> level_of_pos; // level of each position
