@@ -42,7 +42,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     deps = [d for d in deps if not d.endswith("pybind_core.cpp")]
     if force or _newer(LIB, deps):
         cmd = [NVCC, "-O3", "-std=c++17", *ARCH_FLAGS, "-lineinfo", "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-O3,-Wall",
-               "-shared", "-cudart", "static", "-o", LIB,
+               "-shared", "-cudart", "static", "-o", LIB, *os.environ.get("MCDP_NVCC_EXTRA", "").split(),
                os.path.join(CSRC, "mcdp_capi.cu"), os.path.join(CSRC, "mcdp_plan.cpp")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

@@ -106,9 +106,7 @@ __device__ __forceinline__ float uniform23(uint32_t w) {
 // the draw -- while the variate itself, x = d * v^3 * scale, is formed in fp64.  Returns true
 // when the attempt is accepted and x <= max_scale (the reference's outer `while (x > max_scale)`
 // loop, _core.cpp:98-104, simply continues the attempt sequence).
-__device__ __forceinline__ bool gamma_attempt(const DistRec& d, uint32_t seed, uint32_t act, uint32_t t,
-                                              const PhiloxKeys& key0, double& x) {
-    const Philox4 w = philox4x32_10(seed, act, t, kTagSolo, key0);
+__device__ __forceinline__ bool gamma_eval(const DistRec& d, const Philox4& w, double& x) {
     const float r2 = -1.3862943611198906f * lg2_approx(uniform23(w.x));           // -2 ln u1
     const float ang = float(int(w.y)) * 1.4629180792671596e-9f;                    // 2 pi * int32 / 2^32, [-pi, pi)
     const float nf = sqrt_approx(fmaxf(r2, 0.0f)) * cos_approx(ang);
@@ -135,15 +133,18 @@ __device__ __forceinline__ bool gamma_attempt(const DistRec& d, uint32_t seed, u
 // pending sample, so a rejection costs the warp one extra attempt instead of one per sample.
 __device__ __forceinline__ void gamma_variate2(const DistRec& d, uint32_t seed_a, uint32_t seed_b, uint32_t act,
                                                const PhiloxKeys& key0, double& xa, double& xb) {
-    bool need_a = !gamma_attempt(d, seed_a, act, 0u, key0, xa);
-    bool need_b = !gamma_attempt(d, seed_b, act, 0u, key0, xb);
+    // both first-attempt blocks are generated back to back: two independent multiply chains in flight
+    const Philox4 wa = philox4x32_10(seed_a, act, 0u, kTagSolo, key0);
+    const Philox4 wb = philox4x32_10(seed_b, act, 0u, kTagSolo, key0);
+    bool need_a = !gamma_eval(d, wa, xa);
+    bool need_b = !gamma_eval(d, wb, xb);
     uint32_t ta = 1u, tb = 1u;
     while (__any_sync(0xFFFFFFFFu, need_a || need_b)) {
         const bool do_a = need_a;
         const uint32_t seed = do_a ? seed_a : seed_b;
         const uint32_t t = do_a ? ta : tb;
         double x;
-        const bool ok = gamma_attempt(d, seed, act, t, key0, x);
+        const bool ok = gamma_eval(d, philox4x32_10(seed, act, t, kTagSolo, key0), x);
         const bool give_up = t + 1u >= kGammaMaxAttempts;  // the reference would spin forever: clamp
         if (give_up) x = fmin(x, d.p[2]);
         if (do_a) {

@@ -237,10 +237,11 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
             const int4 e0 = __ldg(reinterpret_cast<const int4*>(p.events + i));
             const int4 e1 = __ldg(reinterpret_cast<const int4*>(p.events + i) + 1);
             if (dyn) {
-                // the warps of a group walk the level's records front to back: pull the lines a sibling
-                // warp will need about one round from now into this SM's L1
-                prefetch_l1(p.events + min(i + wpg, p.E - 1));
-                prefetch_l1(p.preds + min(uint32_t(e0.z) + 4u * uint32_t(wpg), p.last_pred));
+                // this warp's next event is already known: pull its record, and (estimating four entries
+                // per event in between) its first entry records, into this SM's L1 while event i runs
+                const int in = min(i_next, p.E - 1);
+                prefetch_l1(p.events + in);
+                prefetch_l1(p.preds + min(uint32_t(e0.z) + uint32_t(e0.w) + 4u * uint32_t(in - i - 1), p.last_pred));
             }
             if constexpr (MODE != kModeReduced) {
                 double ra, rb;
