@@ -31,7 +31,7 @@ WORKLOADS = {
     # name: (generator, per-GPU samples per step (full mode), e2e samples per step, description)
     "c1": ("c1_toy", 1 << 20, 1 << 18, "toy demo DAG 10 events / 12 activities, 200-point empirical tables"),
     "c2": ("c2_layered", 1 << 18, 1 << 15, "layered timetable DAG 10k events / 30k activities, exponential delays"),
-    "c3": ("c3_network", 18944, 1 << 12, "network DAG 100k events / 400k activities, gamma + empirical-relative"),
+    "c3": ("c3_network", 18944, 1 << 11, "network DAG 100k events / 400k activities, gamma + empirical-relative"),
     "c4": ("c4_national", 1 << 15, 1 << 15, "national DAG 1M events / 4M activities (reduced statistics mode)"),
     "c5": ("c5_deep_chain", 1 << 18, 1 << 18, "50k-event chain + 200 merge nodes fan-in 256 (reduced statistics mode)"),
 }

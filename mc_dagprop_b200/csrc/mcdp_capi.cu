@@ -211,21 +211,25 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false,
     return s;
 }
 
+template <typename K>
+int32_t launch_kernel(K k, const SweepParams& p, const LaunchShape& s, cudaStream_t stream) {
+    if (s.smem > 48 * 1024) MCDP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s.smem)));
+    k<<<s.grid, s.threads, s.smem, stream>>>(p);
+    MCDP_CUDA(cudaGetLastError());
+    return MCDP_OK;
+}
+
 template <int MODE>
 int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p, const LaunchShape& s, cudaStream_t stream) {
-    if (p.n <= 0) return MCDP_OK;
-    if (s.smem_tables) {
-        auto k = sweep_kernel<MODE, true>;
-        if (s.smem > 48 * 1024) MCDP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s.smem)));
-        k<<<s.grid, s.threads, s.smem, stream>>>(p);
-    } else {
-        auto k = sweep_kernel<MODE, false>;
-        if (s.smem > 48 * 1024) MCDP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s.smem)));
-        k<<<s.grid, s.threads, s.smem, stream>>>(p);
-    }
-    MCDP_CUDA(cudaGetLastError());
     (void)plan;
-    return MCDP_OK;
+    if (p.n <= 0) return MCDP_OK;
+    if constexpr (MODE == kModeReduced) {
+        if (s.batches > 1)
+            return s.smem_tables ? launch_kernel(sweep_kernel<MODE, true, true>, p, s, stream)
+                                 : launch_kernel(sweep_kernel<MODE, false, true>, p, s, stream);
+    }
+    return s.smem_tables ? launch_kernel(sweep_kernel<MODE, true, false>, p, s, stream)
+                         : launch_kernel(sweep_kernel<MODE, false, false>, p, s, stream);
 }
 
 SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, int64_t ld) {

@@ -70,7 +70,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 // std::min(a, b) of the reference build: (b < a) ? b : a  -- NOT fmin (NaN / signed-zero differ).
 __device__ __forceinline__ double ref_min(double a, double b) { return (b < a) ? b : a; }
 
-template <int MODE, bool SMEM>
+// MULTI (reduced mode only): a group folds several 64-sample batches per event before flushing.
+template <int MODE, bool SMEM, bool MULTI = false>
 __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kernel(const __grid_constant__ SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DistRec* dists = p.dists;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
     // reduced mode: one private histogram per warp, flushed once per event
     uint32_t* w_hist = nullptr;
     if constexpr (MODE == kModeReduced) {
-        if (p.hist && p.batches_per_group > 1) {
+        if (MULTI && p.hist) {
             uint32_t* all = reinterpret_cast<uint32_t*>(smem_raw + ((smem_used + 15) & ~size_t(15)));
             for (int i = threadIdx.x; i < int(blockDim.x >> 5) * p.n_bins; i += blockDim.x) all[i] = 0u;
             w_hist = all + warp * p.n_bins;
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
     const int groups_per_cta = (blockDim.x >> 5) / wpg;
     // A group owns `batches` consecutive 64-sample batches (1 except in reduced mode, where a warp
     // folds the statistics of all its batches before touching the global accumulators).
-    const int batches = MODE == kModeReduced ? p.batches_per_group : 1;
+    const int batches = (MODE == kModeReduced && MULTI) ? p.batches_per_group : 1;
     const int64_t batch0 = (int64_t(blockIdx.x) * groups_per_cta + group_in_cta) * batches;
     if (batch0 * 64 >= p.n) return;  // whole group (all its warps) out of range
     const PhiloxKeys& key0 = p.keys;
