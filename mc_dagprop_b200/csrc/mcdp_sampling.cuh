@@ -83,16 +83,23 @@ __device__ __forceinline__ uint32_t guide_ld(const uint32_t* p) {
 // random.tcc:2709-2713): the guide table (four buckets per entry) gives the first candidate, one
 // unconditional compare-and-step follows, and a scan loop that almost never iterates finishes.
 template <bool SMEM>
-__device__ __forceinline__ double emp_value(const char* guide_b, const char* cp_b, uint32_t g, uint32_t len8, bool scan,
-                                            uint32_t hi, double u) {
-    // floor(u * 2^g) == (X >> 12) >> (52 - g) == hi >> (32 - g),  1 <= g <= 20
-    const uint32_t j = hi >> (32u - g);
-    uint32_t off = guide_ld<SMEM>(reinterpret_cast<const uint32_t*>(guide_b) + j) * 8u;
-    if (tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off)) < u) off += 8u;  // cp[len-1] == 1.0 > u: stays in range
+__device__ __forceinline__ void emp_value2(const char* guide_b, const char* cp_b, uint32_t g, uint32_t len8, bool scan,
+                                           uint32_t hi_a, double ua, uint32_t hi_b, double ub, double& va, double& vb) {
+    // floor(u * 2^g) == (X >> 12) >> (52 - g) == hi >> (32 - g),  1 <= g <= 20.  The two samples of
+    // the lane are looked up in lockstep (one basic block) so their shared-memory latencies overlap.
+    const uint32_t ja = hi_a >> (32u - g), jb = hi_b >> (32u - g);
+    uint32_t off_a = guide_ld<SMEM>(reinterpret_cast<const uint32_t*>(guide_b) + ja) * 8u;
+    uint32_t off_b = guide_ld<SMEM>(reinterpret_cast<const uint32_t*>(guide_b) + jb) * 8u;
+    const double ca = tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_a));
+    const double cb = tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_b));
+    off_a += ca < ua ? 8u : 0u;  // cp[len-1] == 1.0 > u: stays in range
+    off_b += cb < ub ? 8u : 0u;
     if (scan) {  // only tables whose guide buckets may hold several boundaries
-        while (tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off)) < u) off += 8u;
+        while (tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_a)) < ua) off_a += 8u;
+        while (tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_b)) < ub) off_b += 8u;
     }
-    return tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off + len8));
+    va = tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_a + len8));
+    vb = tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_b + len8));
 }
 
 // (k + 1/2) * 2^-23 for the top 23 bits k of w: an fp32 uniform strictly inside (0,1), exact.
@@ -106,26 +113,54 @@ __device__ __forceinline__ float uniform23(uint32_t w) {
 // the draw -- while the variate itself, x = d * v^3 * scale, is formed in fp64.  Returns true
 // when the attempt is accepted and x <= max_scale (the reference's outer `while (x > max_scale)`
 // loop, _core.cpp:98-104, simply continues the attempt sequence).
-__device__ __forceinline__ bool gamma_eval(const DistRec& d, const Philox4& w, double& x) {
-    const float r2 = -1.3862943611198906f * lg2_approx(uniform23(w.x));           // -2 ln u1
-    const float ang = float(int(w.y)) * 1.4629180792671596e-9f;                    // 2 pi * int32 / 2^32, [-pi, pi)
-    const float nf = sqrt_approx(fmaxf(r2, 0.0f)) * cos_approx(ang);
-    const double n = double(nf);
-    double v = fma(d.p[4], n, 1.0);
-    const bool pos = v > 0.0;
-    v = v * v * v;
-    const float u = uniform23(w.z);
-    const float n2 = nf * nf;
-    bool ok = u <= fmaf(-0.0331f * n2, n2, 1.0f);
-    if (!ok) {
-        const float vf = float(v);
-        const float a1f = float(d.p[3]);
-        // log(u) <= n^2/2 + d (1 - v + log v)
-        ok = 0.6931471805599453f * lg2_approx(u) <= fmaf(0.5f, n2, a1f * (1.0f - vf + 0.6931471805599453f * lg2_approx(vf)));
-    }
-    x = d.p[6] * v;  // d * scale * v^3
+struct GammaHalf {  // the fp32-steered part of one attempt, split so that two attempts can run in lockstep
+    float nf, n2, u;
+    double v;
+    bool pos, ok;
+};
+__device__ __forceinline__ void gamma_front(const DistRec& d, const Philox4& w, GammaHalf& h) {
+    const float r2 = -1.3862943611198906f * lg2_approx(uniform23(w.x));  // -2 ln u1
+    const float ang = float(int(w.y)) * 1.4629180792671596e-9f;           // 2 pi * int32 / 2^32, [-pi, pi)
+    h.nf = sqrt_approx(fmaxf(r2, 0.0f)) * cos_approx(ang);
+    double v = fma(d.p[4], double(h.nf), 1.0);
+    h.pos = v > 0.0;
+    h.v = v * v * v;
+    h.u = uniform23(w.z);
+    h.n2 = h.nf * h.nf;
+    h.ok = h.u <= fmaf(-0.0331f * h.n2, h.n2, 1.0f);
+}
+__device__ __forceinline__ void gamma_exact(const DistRec& d, GammaHalf& h) {
+    // log(u) <= n^2/2 + d (1 - v + log v)
+    const float vf = float(h.v);
+    h.ok = 0.6931471805599453f * lg2_approx(h.u) <=
+           fmaf(0.5f, h.n2, float(d.p[3]) * (1.0f - vf + 0.6931471805599453f * lg2_approx(vf)));
+}
+__device__ __forceinline__ bool gamma_back(const DistRec& d, const Philox4& w, const GammaHalf& h, double& x) {
+    x = d.p[6] * h.v;  // d * scale * v^3
     if (d.flags & 1) x *= double(ex2_approx(lg2_approx(uniform23(w.w)) * float(d.p[5])));  // u^(1/shape), shape < 1
-    return pos && ok && x <= d.p[2];
+    return h.pos && h.ok && x <= d.p[2];
+}
+__device__ __forceinline__ bool gamma_eval(const DistRec& d, const Philox4& w, double& x) {
+    GammaHalf h;
+    gamma_front(d, w, h);
+    if (!h.ok) gamma_exact(d, h);
+    return gamma_back(d, w, h, x);
+}
+// two attempts at once: one shared branch for the exact test, everything else straight-line
+__device__ __forceinline__ void gamma_eval2(const DistRec& d, const Philox4& wa, const Philox4& wb, double& xa,
+                                            double& xb, bool& ok_a, bool& ok_b) {
+    GammaHalf ha, hb;
+    gamma_front(d, wa, ha);
+    gamma_front(d, wb, hb);
+    if (!(ha.ok && hb.ok)) {
+        const bool sa = ha.ok, sb = hb.ok;
+        gamma_exact(d, ha);
+        gamma_exact(d, hb);
+        ha.ok = ha.ok || sa;  // a passed squeeze test stays accepted
+        hb.ok = hb.ok || sb;
+    }
+    ok_a = gamma_back(d, wa, ha, xa);
+    ok_b = gamma_back(d, wb, hb, xb);
 }
 
 // Gamma variates for the two samples of a thread.  First attempts run straight-line for both
@@ -136,8 +171,10 @@ __device__ __forceinline__ void gamma_variate2(const DistRec& d, uint32_t seed_a
     // both first-attempt blocks are generated back to back: two independent multiply chains in flight
     const Philox4 wa = philox4x32_10(seed_a, act, 0u, kTagSolo, key0);
     const Philox4 wb = philox4x32_10(seed_b, act, 0u, kTagSolo, key0);
-    bool need_a = !gamma_eval(d, wa, xa);
-    bool need_b = !gamma_eval(d, wb, xb);
+    bool need_a, need_b;
+    gamma_eval2(d, wa, wb, xa, xb, need_a, need_b);
+    need_a = !need_a;
+    need_b = !need_b;
     uint32_t ta = 1u, tb = 1u;
     while (__any_sync(0xFFFFFFFFu, need_a || need_b)) {
         const bool do_a = need_a;
@@ -207,9 +244,14 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, c
         // reference's rejection loop (_core.cpp:83-89), without the loop.
         const DistRec& d = dists[dist];
         const double lam = d.p[0], mx = d.p[1], F = d.p[2];
-        const bool tiny = d.flags & 2;
-        double xa = lam * neg_log1m(ua * F, tiny);
-        double xb = lam * neg_log1m(ub * F, tiny);
+        double xa, xb;
+        if (d.flags & 2) {  // F < 2^-10: series keeps the relative accuracy (both samples in one block)
+            xa = lam * neg_log1m(ua * F, true);
+            xb = lam * neg_log1m(ub * F, true);
+        } else {
+            xa = lam * neg_log1m(ua * F, false);
+            xb = lam * neg_log1m(ub * F, false);
+        }
         xa = xa > mx ? mx : xa;
         xb = xb > mx ? mx : xb;
         ea = __dmul_rn(xa, base);
@@ -222,8 +264,8 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, c
     const bool scan = meta & 0x800000u;
     const char* guide_b = reinterpret_cast<const char*>(tab) + tab_off;
     const char* cp_b = reinterpret_cast<const char*>(tab) + dist;
-    const double va = emp_value<SMEM>(guide_b, cp_b, g, len8, scan, hi_a, ua);
-    const double vb = emp_value<SMEM>(guide_b, cp_b, g, len8, scan, hi_b, ub);
+    double va, vb;
+    emp_value2<SMEM>(guide_b, cp_b, g, len8, scan, hi_a, ua, hi_b, ub, va, vb);
     if (kind == MCDP_DIST_EMP_ABS) {  // _core.cpp:125
         ea = va;
         eb = vb;
