@@ -36,7 +36,7 @@ def c1_toy(variant: str = "empirical"):
         for i, sc in enumerate(scales):
             dists.add_empirical_absolute(i, np.arange(200.0), _discretised_exponential(sc))
     elif variant == "const_exp":
-        acts = [(i, float(earliest[d] - earliest[s]), i) for i, (s, d) in enumerate(edges)]
+        acts = [(i, max(0.0, float(earliest[d] - earliest[s])), i) for i, (s, d) in enumerate(edges)]
         for i, sc in enumerate(scales):
             if i % 3 == 0:
                 dists.add_constant(i, 0.1)
