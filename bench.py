@@ -316,6 +316,26 @@ def run_b200(args):
         e2e = {"value": world * ne * A * ke / dt, "unit": "edge-samples/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "samples_per_step": ne, "steps": ke,
                "api": "mcdp_run_reduced_host" if reduced else "mcdp_run_many_host (pinned host buffers)"}
+        if not reduced:
+            # for information: the same DAG through the statistics API (host seeds in, per-event mean / variance /
+            # lateness counts / 64-bin histogram out) -- what a caller who does not need every sample would use
+            nr = n
+            th = (60.0, 180.0, 300.0)
+            seeds_r = np.arange(nr, dtype=np.int32)
+            plan.run_reduced_host(seeds_r, thresholds=th, n_bins=64, hist_range=(0.0, dag.max_delay))
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            for i in range(ke):
+                plan.run_reduced_host(seeds_r + i * nr, thresholds=th, n_bins=64, hist_range=(0.0, dag.max_delay))
+            dtr = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([dtr], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dtr = float(t.item())
+            e2e["reduced_api"] = {"value": world * nr * A * ke / dtr, "unit": "edge-samples/s", "samples_per_step": nr,
+                                  "h2d_bytes_per_step": 4 * nr, "d2h_bytes_per_step": E * (8 + 8 + 3 * 8 + 64 * 4),
+                                  "api": "mcdp_run_reduced_host"}
 
     if rank == 0:
         cb = None
