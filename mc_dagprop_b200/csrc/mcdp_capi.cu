@@ -96,15 +96,22 @@ struct mcdp_plan {
     int sm_count = 148;
     size_t smem_optin = 0;
     // device-resident stream
-    DevBuf<EventRec> d_events;
-    DevBuf<PredRec> d_preds;
+    // event + precedence records live in ONE allocation so that a single L2 access-policy window
+    // (persisting) covers the whole stream: 128 GB of streaming output per launch would otherwise
+    // keep evicting the records every warp re-reads
+    DevBuf<unsigned char> d_stream, d_stream_red;
+    size_t l2_persist_bytes = 0, l2_window_max = 0;
+    struct RecPtrs {
+        EventRec* p = nullptr;
+    } d_events, d_events_red;
+    struct PredPtrs {
+        PredRec* p = nullptr;
+    } d_preds, d_preds_red;
     DevBuf<int32_t> d_level_begin;
     DevBuf<PredRec> d_orphans;
     DevBuf<DistRec> d_dists;
     DevBuf<double> d_tab;
     // reduced-mode variant of the stream (rows = recycled scratch slots), built on first use
-    DevBuf<EventRec> d_events_red;
-    DevBuf<PredRec> d_preds_red;
     DevBuf<double> d_scratch;
     bool red_ready = false;
     // options
@@ -124,14 +131,12 @@ struct mcdp_plan {
     ~mcdp_plan() {
         DeviceGuard g(device);
         for (auto& s : slots) s.release();
-        d_events.release();
-        d_preds.release();
+        d_stream.release();
+        d_stream_red.release();
         d_level_begin.release();
         d_orphans.release();
         d_dists.release();
         d_tab.release();
-        d_events_red.release();
-        d_preds_red.release();
         d_scratch.release();
         d_acts.release();
         d_norm_cache.release();
@@ -147,6 +152,18 @@ template <typename T>
 int32_t upload(DevBuf<T>& buf, const std::vector<T>& v) {
     MCDP_CUDA(buf.ensure(v.size()));
     if (!v.empty()) MCDP_CUDA(cudaMemcpy(buf.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return MCDP_OK;
+}
+
+// events then precedence records, back to back in one allocation
+int32_t upload_stream(DevBuf<unsigned char>& pool, const std::vector<EventRec>& ev, const std::vector<PredRec>& pr,
+                      EventRec** d_ev, PredRec** d_pr) {
+    const size_t eb = ev.size() * sizeof(EventRec), pb = pr.size() * sizeof(PredRec);
+    MCDP_CUDA(pool.ensure(eb + pb));
+    *d_ev = reinterpret_cast<EventRec*>(pool.p);
+    *d_pr = reinterpret_cast<PredRec*>(pool.p + eb);
+    if (eb) MCDP_CUDA(cudaMemcpy(*d_ev, ev.data(), eb, cudaMemcpyHostToDevice));
+    if (pb) MCDP_CUDA(cudaMemcpy(*d_pr, pr.data(), pb, cudaMemcpyHostToDevice));
     return MCDP_OK;
 }
 
@@ -212,24 +229,44 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false,
 }
 
 template <typename K>
-int32_t launch_kernel(K k, const SweepParams& p, const LaunchShape& s, cudaStream_t stream) {
+int32_t launch_kernel(mcdp_plan* plan, K k, const SweepParams& p, const LaunchShape& s, cudaStream_t stream) {
     if (s.smem > 48 * 1024) MCDP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s.smem)));
-    k<<<s.grid, s.threads, s.smem, stream>>>(p);
-    MCDP_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(s.grid);
+    cfg.blockDim = dim3(unsigned(s.threads));
+    cfg.dynamicSmemBytes = s.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    unsigned n_attr = 0;
+    const size_t stream_bytes = size_t(plan->host.E) * sizeof(EventRec) + size_t(plan->host.P) * sizeof(PredRec);
+    if (plan->l2_persist_bytes > 0 && plan->l2_window_max > 0 && stream_bytes > 0) {
+        // the event / precedence records are re-read by every warp while >100 GB of outputs stream through
+        // L2: pin them with a persisting access-policy window (events and records are one allocation)
+        const size_t win = std::min(stream_bytes, plan->l2_window_max);
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<EventRec*>(p.events);
+        attr[0].val.accessPolicyWindow.num_bytes = win;
+        attr[0].val.accessPolicyWindow.hitRatio = float(std::min(1.0, double(plan->l2_persist_bytes) / double(win)));
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        n_attr = 1;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n_attr;
+    MCDP_CUDA(cudaLaunchKernelEx(&cfg, k, p));
     return MCDP_OK;
 }
 
 template <int MODE>
 int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p, const LaunchShape& s, cudaStream_t stream) {
-    (void)plan;
     if (p.n <= 0) return MCDP_OK;
     if constexpr (MODE == kModeReduced) {
         if (s.batches > 1)
-            return s.smem_tables ? launch_kernel(sweep_kernel<MODE, true, true>, p, s, stream)
-                                 : launch_kernel(sweep_kernel<MODE, false, true>, p, s, stream);
+            return s.smem_tables ? launch_kernel(plan, sweep_kernel<MODE, true, true>, p, s, stream)
+                                 : launch_kernel(plan, sweep_kernel<MODE, false, true>, p, s, stream);
     }
-    return s.smem_tables ? launch_kernel(sweep_kernel<MODE, true, false>, p, s, stream)
-                         : launch_kernel(sweep_kernel<MODE, false, false>, p, s, stream);
+    return s.smem_tables ? launch_kernel(plan, sweep_kernel<MODE, true, false>, p, s, stream)
+                         : launch_kernel(plan, sweep_kernel<MODE, false, false>, p, s, stream);
 }
 
 SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, int64_t ld) {
@@ -287,9 +324,7 @@ int32_t ensure_reduced_stream(mcdp_plan* plan) {
         for (uint32_t k = 0; k < e.fan_in; ++k)
             pr[e.pred_begin + k].next_src_row = k + 1 < e.fan_in ? pr[e.pred_begin + k + 1].src_row : 0u;
     }
-    int32_t rc = upload(plan->d_events_red, ev);
-    if (rc) return rc;
-    rc = upload(plan->d_preds_red, pr);
+    int32_t rc = upload_stream(plan->d_stream_red, ev, pr, &plan->d_events_red.p, &plan->d_preds_red.p);
     if (rc) return rc;
     plan->red_ready = true;
     return MCDP_OK;
@@ -388,10 +423,18 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
         plan->sm_count = prop.multiProcessorCount;
         plan->smem_optin = prop.sharedMemPerBlockOptin;
+        plan->l2_window_max = size_t(std::max(prop.accessPolicyMaxWindowSize, 0));
+        // set aside L2 for the record stream (device-wide limit; the last plan created decides)
+        const size_t stream_bytes = plan->host.events.size() * sizeof(EventRec) + plan->host.preds.size() * sizeof(PredRec);
+        const size_t want = std::min<size_t>({stream_bytes + (stream_bytes >> 3) + (1u << 20),
+                                             size_t(std::max(prop.persistingL2CacheMaxSize, 0)), size_t(64) << 20});
+        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+            plan->l2_persist_bytes = want;
+        else
+            cudaGetLastError();
     }
     const HostPlan& h = plan->host;
-    int32_t rc = upload(plan->d_events, h.events);
-    if (!rc) rc = upload(plan->d_preds, h.preds);
+    int32_t rc = upload_stream(plan->d_stream, h.events, h.preds, &plan->d_events.p, &plan->d_preds.p);
     if (!rc) rc = upload(plan->d_level_begin, h.level_begin);
     if (!rc) rc = upload(plan->d_orphans, h.orphans);
     if (!rc) rc = upload(plan->d_dists, h.dists);

@@ -132,12 +132,12 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
         // drawn (its source row is carried by the event record / the current entry record), so the
         // HBM latency of the gather hides behind the sampling arithmetic.
         double2 nrs = make_double2(0.0, 0.0);
-        if (fan_in) nrs = *reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(e1.z)) * ldb8);
+        if (fan_in) nrs = __ldcg(reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(e1.z)) * ldb8));
         for (uint32_t k = 0; k < fan_in; ++k, ++pr) {
             const int4 q0 = __ldg(reinterpret_cast<const int4*>(pr));
             const int4 q1 = __ldg(reinterpret_cast<const int4*>(pr) + 1);
             const double2 rs = nrs;
-            if (k + 1 < fan_in) nrs = *reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(q1.z)) * ldb8);
+            if (k + 1 < fan_in) nrs = __ldcg(reinterpret_cast<const double2*>(r_lane + size_t(uint32_t(q1.z)) * ldb8));
             const uint32_t act = uint32_t(q0.y);
             const double base = __hiloint2double(q0.w, q0.z);
             const uint32_t meta = uint32_t(q1.x);
@@ -177,7 +177,9 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
         // _core.cpp:348-349
         ra = ref_min(lat_a, ub);
         rb = ref_min(lat_b, ub);
-        *reinterpret_cast<double2*>(r_lane + size_t(row) * ldb8) = make_double2(ra, rb);
+        // realized rows are gathered once per consumer, by other warps: keep them out of L1 (L2 only) so
+        // the warp-uniform record lines stay resident there
+        __stcg(reinterpret_cast<double2*>(r_lane + size_t(row) * ldb8), make_double2(ra, rb));
         if constexpr (MODE != kModeReduced)
             __stcs(reinterpret_cast<int2*>(c_lane + size_t(row) * ldb4), make_int2(cause_a, cause_b));
     };
