@@ -74,6 +74,15 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                 r.p[5] = 1.0 / p0;
                 r.p[6] = a1 * p1;
                 r.flags = p0 < 1.0 ? 1 : 0;
+                {
+                    // 2 * shape in {1..8}: sum of floor(shape) exponentials (+ half a squared normal) is exact
+                    const double twice = 2.0 * p0;
+                    if (twice == std::floor(twice) && twice >= 1.0 && twice <= 8.0) {
+                        r.flags |= 8;
+                        r.pad0 = int32_t(std::floor(p0));
+                        r.pad1 = int32_t(twice) & 1;
+                    }
+                }
                 break;
             }
             case MCDP_DIST_EMP_ABS:

@@ -67,7 +67,8 @@ struct alignas(16) DistRec {
     int32_t tab_len;
     int32_t tab_off;
     int32_t guide_log2;
-    int32_t flags;      // bit0 gamma shape < 1, bit1 exponential series, bit2 table needs the scan loop
+    int32_t flags;      // bit0 gamma shape < 1, bit1 exponential series, bit2 table needs the scan loop,
+                        // bit3 gamma with 2*shape in 1..8 (exact transformation: pad0 = floor(shape), pad1 = half term)
     int32_t pad0, pad1, pad2;
     double p[8];
 };

@@ -67,6 +67,11 @@ __device__ __forceinline__ double uniform52(uint32_t lo, uint32_t hi) {
     return __hiloint2double(static_cast<int>(0x3FF00000u | khi), static_cast<int>(klo)) - (1.0 - 0x1p-53);
 }
 
+// (w + 0.5) * 2^-32 in (0,1), exact.
+__device__ __forceinline__ double uniform32(uint32_t w) {
+    return __hiloint2double(0x41300000, static_cast<int>(w)) - (1048576.0 - 0x1p-33);
+}
+
 // Table access: SMEM => the pool pointer addresses shared memory (staged copy), else global (L1/L2).
 template <bool SMEM>
 __device__ __forceinline__ double tab_ld(const double* p) {
@@ -200,6 +205,79 @@ __device__ __forceinline__ void gamma_variate2(const DistRec& d, uint32_t seed_a
     }
 }
 
+// Gamma with 2 * shape in {1, ..., 8}: exact transformation without rejection.
+//   Gamma(k + h/2, scale) = scale * ( -ln(u_1 ... u_k)  +  h * (-ln u') cos^2(2 pi u'') ),   k = floor(shape), h in {0,1}
+// (a sum of k unit exponentials plus, for half-integer shapes, half the square of a Box-Muller
+// normal).  The logs are fp64 (log_pos), cos is the fp32 hardware approximation.  Up to two 32-bit
+// uniforms per sample come from a PAIR-style block shared by the seed pair, three or four from a
+// block per seed; draw j + 1 is used when x > max_scale (the reference's outer redraw loop,
+// _core.cpp:98-104).
+constexpr uint32_t kTagErlang = 0x45524C47u;  // 'ERLG'
+
+__device__ __forceinline__ double erlang_value(const DistRec& d, int k, bool half, uint32_t w0, uint32_t w1, uint32_t w2,
+                                               uint32_t w3) {
+    // words are consumed in order: k product uniforms, then (u', u'') of the half term
+    double e = 0.0;
+    if (k > 0) {
+        double prod = uniform32(w0);
+        if (k > 1) prod *= uniform32(w1);
+        if (k > 2) prod *= uniform32(w2);
+        if (k > 3) prod *= uniform32(w3);
+        e = -log_pos(prod);
+    }
+    if (half) {
+        const uint32_t wu = k == 0 ? w0 : (k == 1 ? w1 : w2);
+        const uint32_t wa = k == 0 ? w1 : (k == 1 ? w2 : w3);
+        const float c = cos_approx(float(int(wa)) * 1.4629180792671596e-9f);  // cos(2 pi * int32 / 2^32)
+        e = fma(-log_pos(uniform32(wu)), double(c * c), e);
+    }
+    return d.p[1] * e;
+}
+
+__device__ __forceinline__ void erlang_variate2(const DistRec& d, uint32_t seed_a, uint32_t seed_b, bool paired,
+                                                uint32_t act, const PhiloxKeys& key0, double& xa, double& xb) {
+    const int k = d.pad0;
+    const bool half = d.pad1 != 0;
+    const bool shared_block = k + 2 * int(half) <= 2;  // <= 64 bits per sample
+    const double mx = d.p[2];
+    uint32_t ja = 0u, jb = 0u;
+    bool need_a = true, need_b = true;
+    for (;;) {
+        double ya, yb;
+        if (shared_block) {
+            if (paired && ja == jb) {
+                const Philox4 r = philox4x32_10(seed_a >> 1, act, ja, kTagErlang, key0);
+                ya = erlang_value(d, k, half, r.x, r.y, 0u, 0u);
+                yb = erlang_value(d, k, half, r.z, r.w, 0u, 0u);
+            } else {
+                const Philox4 ra = philox4x32_10(seed_a >> 1, act, ja, kTagErlang, key0);
+                const Philox4 rb = philox4x32_10(seed_b >> 1, act, jb, kTagErlang, key0);
+                const bool oa = seed_a & 1u, ob = seed_b & 1u;
+                ya = erlang_value(d, k, half, oa ? ra.z : ra.x, oa ? ra.w : ra.y, 0u, 0u);
+                yb = erlang_value(d, k, half, ob ? rb.z : rb.x, ob ? rb.w : rb.y, 0u, 0u);
+            }
+        } else {
+            const Philox4 ra = philox4x32_10(seed_a, act, ja, kTagErlang, key0);
+            const Philox4 rb = philox4x32_10(seed_b, act, jb, kTagErlang, key0);
+            ya = erlang_value(d, k, half, ra.x, ra.y, ra.z, ra.w);
+            yb = erlang_value(d, k, half, rb.x, rb.y, rb.z, rb.w);
+        }
+        if (need_a) {
+            xa = ya;
+            need_a = ya > mx && ja + 1u < kGammaMaxAttempts;
+            ja += need_a ? 1u : 0u;
+        }
+        if (need_b) {
+            xb = yb;
+            need_b = yb > mx && jb + 1u < kGammaMaxAttempts;
+            jb += need_b ? 1u : 0u;
+        }
+        if (!__any_sync(0xFFFFFFFFu, need_a || need_b)) break;
+    }
+    xa = xa > mx ? mx : xa;  // only after the attempt cap
+    xb = xb > mx ? mx : xb;
+}
+
 // Extra delays of one activity for the two samples a thread owns.  `meta`/`tab_off` come from the
 // precedence record (kind, guide bits, table length / pool block).  `paired`: the seeds are
 // {2k, 2k+1}, so one PAIR block serves both.  Returns extra (the value Dist::sample returns); the
@@ -216,7 +294,10 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, c
     }
     if (kind == MCDP_DIST_GAMMA) {
         double xa, xb;
-        gamma_variate2(dists[dist], seed_a, seed_b, act, key0, xa, xb);
+        if (dists[dist].flags & 8)
+            erlang_variate2(dists[dist], seed_a, seed_b, paired, act, key0, xa, xb);
+        else
+            gamma_variate2(dists[dist], seed_a, seed_b, act, key0, xa, xb);
         ea = __dmul_rn(xa, base);
         eb = __dmul_rn(xb, base);
         return;

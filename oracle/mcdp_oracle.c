@@ -488,9 +488,11 @@ void mcdp_or_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_
 #define SPEC_TAG_PAIR 0x50414952u /* 'PAIR' */
 #define SPEC_TAG_SOLO 0x534F4C4Fu /* 'SOLO' */
 #define SPEC_KEY1 0x4D434450u     /* 'MCDP' */
+#define SPEC_TAG_ERLANG 0x45524C47u /* 'ERLG' */
 #define SPEC_GAMMA_MAX_ATTEMPTS 65536u
 
 static double spec_u52(uint64_t x) { return ((double)(x >> 12) + 0.5) * 0x1p-52; }
+static double spec_u32(uint32_t w) { return ((double)w + 0.5) * 0x1p-32; }
 static double spec_u23(uint32_t w) { return ((double)(w >> 9) + 0.5) * 0x1p-23; }
 
 /* 64 random bits of (activity, seed, draw j): one Philox block serves the seed pair {2k, 2k+1} */
@@ -523,6 +525,40 @@ static double spec_sample_extra(const or_dist* d, double base, uint32_t act, uin
             const double a1 = d->malpha - 1.0 / 3.0;
             const uint32_t key[2] = {stream_key, SPEC_KEY1};
             double x = 0.0;
+            const double twice = 2.0 * d->p0;
+            if (twice == floor(twice) && twice >= 1.0 && twice <= 8.0) {
+                /* exact transformation for 2*shape in 1..8: k = floor(shape) unit exponentials (+ half a squared
+                 * Box-Muller normal); <= 2 uniforms: the seed's half of block (seed>>1, act, j, 'ERLG'), else the
+                 * four words of block (seed, act, j, 'ERLG'); draw j+1 when x > max_scale */
+                const int k = (int)floor(d->p0), half = ((int)twice) & 1;
+                for (uint32_t j = 0; j < SPEC_GAMMA_MAX_ATTEMPTS; ++j) {
+                    uint32_t w[4], r[4];
+                    if (k + 2 * half <= 2) {
+                        const uint32_t ctr[4] = {seed >> 1, act, j, SPEC_TAG_ERLANG};
+                        mcdp_or_philox4x32_10(ctr, key, r);
+                        w[0] = (seed & 1u) ? r[2] : r[0];
+                        w[1] = (seed & 1u) ? r[3] : r[1];
+                        w[2] = w[3] = 0u;
+                    } else {
+                        const uint32_t ctr[4] = {seed, act, j, SPEC_TAG_ERLANG};
+                        mcdp_or_philox4x32_10(ctr, key, w);
+                    }
+                    double e = 0.0;
+                    if (k > 0) {
+                        double prod = spec_u32(w[0]);
+                        for (int i = 1; i < k; ++i) prod *= spec_u32(w[i]);
+                        e = -log(prod);
+                    }
+                    if (half) {
+                        const double c = cos(6.283185307179586476925286766559 * (double)(int32_t)w[k + 1] * 0x1p-32);
+                        e += -log(spec_u32(w[k])) * c * c;
+                    }
+                    x = d->p1 * e;
+                    if (x <= d->p2) return x * base;
+                }
+                if (x > d->p2) x = d->p2;
+                return x * base;
+            }
             for (uint32_t t = 0; t < SPEC_GAMMA_MAX_ATTEMPTS; ++t) {
                 const uint32_t ctr[4] = {seed, act, t, SPEC_TAG_SOLO};
                 uint32_t w[4];

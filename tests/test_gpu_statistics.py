@@ -36,6 +36,14 @@ CASES = {
     "gamma_shape_half": lambda d: d.add_gamma(1, 0.5, 0.3, 5.0),
     "gamma_shape_7_untruncated": lambda d: d.add_gamma(1, 7.3, 0.2),
     "gamma_truncated": lambda d: d.add_gamma(1, 2.0, 1.0, 1.5),
+    # 2 * shape in 1..8 takes the exact-transformation path (sum of exponentials + half a squared normal) ...
+    "gamma_shape_1": lambda d: d.add_gamma(1, 1.0, 0.4, 6.0),
+    "gamma_shape_1p5": lambda d: d.add_gamma(1, 1.5, 0.4, 6.0),
+    "gamma_shape_3p5_truncated": lambda d: d.add_gamma(1, 3.5, 0.5, 2.0),
+    "gamma_shape_4": lambda d: d.add_gamma(1, 4.0, 0.25),
+    # ... every other shape Marsaglia-Tsang
+    "gamma_shape_2p3": lambda d: d.add_gamma(1, 2.3, 0.1, 5.0),
+    "gamma_shape_0p6_truncated": lambda d: d.add_gamma(1, 0.6, 0.5, 1.0),
     "empirical_relative_256": lambda d: d.add_empirical_relative(1, np.linspace(0, 3, 256), np.exp(-np.linspace(0, 3, 256))),
     "empirical_absolute_5": lambda d: d.add_empirical_absolute(1, [0.0, 1.0, 2.0, 5.0, 9.0], [0.3, 0.3, 0.2, 0.15, 0.05]),
 }
