@@ -13,7 +13,7 @@
 #include "../../include/mcdp_b200.h"
 #include "mcdp_plan.hpp"
 #include "mcdp_compat.cuh"
-#include "mcdp_sweep.cuh"
+#include "mcdp_chunk_sweep.cuh"
 
 using namespace mcdp;
 
@@ -99,14 +99,16 @@ struct mcdp_plan {
     // event + precedence records live in ONE allocation so that a single L2 access-policy window
     // (persisting) covers the whole stream: 128 GB of streaming output per launch would otherwise
     // keep evicting the records every warp re-reads
-    DevBuf<unsigned char> d_stream, d_stream_red;
+    DevBuf<ChunkUnit> d_chunks;           // full / injected modes
+    DevBuf<int32_t> d_chunk_level_begin;
+    DevBuf<unsigned char> d_stream_red;   // reduced mode: event + precedence records
     size_t l2_persist_bytes = 0, l2_window_max = 0;
     struct RecPtrs {
         EventRec* p = nullptr;
-    } d_events, d_events_red;
+    } d_events_red;
     struct PredPtrs {
         PredRec* p = nullptr;
-    } d_preds, d_preds_red;
+    } d_preds_red;
     DevBuf<int32_t> d_level_begin;
     DevBuf<PredRec> d_orphans;
     DevBuf<DistRec> d_dists;
@@ -131,7 +133,8 @@ struct mcdp_plan {
     ~mcdp_plan() {
         DeviceGuard g(device);
         for (auto& s : slots) s.release();
-        d_stream.release();
+        d_chunks.release();
+        d_chunk_level_begin.release();
         d_stream_red.release();
         d_level_begin.release();
         d_orphans.release();
@@ -229,22 +232,22 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false,
 }
 
 template <typename K>
-int32_t launch_kernel(mcdp_plan* plan, K k, const SweepParams& p, const LaunchShape& s, cudaStream_t stream) {
-    if (s.smem > 48 * 1024) MCDP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(s.smem)));
+int32_t launch_kernel(mcdp_plan* plan, K k, const SweepParams& p, const LaunchShape& s, size_t smem, const void* stream_base,
+                      size_t stream_bytes, cudaStream_t stream) {
+    if (smem > 48 * 1024) MCDP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(s.grid);
     cfg.blockDim = dim3(unsigned(s.threads));
-    cfg.dynamicSmemBytes = s.smem;
+    cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     unsigned n_attr = 0;
-    const size_t stream_bytes = size_t(plan->host.E) * sizeof(EventRec) + size_t(plan->host.P) * sizeof(PredRec);
     if (plan->l2_persist_bytes > 0 && plan->l2_window_max > 0 && stream_bytes > 0) {
-        // the event / precedence records are re-read by every warp while >100 GB of outputs stream through
-        // L2: pin them with a persisting access-policy window (events and records are one allocation)
+        // the plan stream is re-read by every group while >100 GB of outputs stream through L2: pin it with a
+        // persisting access-policy window
         const size_t win = std::min(stream_bytes, plan->l2_window_max);
         attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = const_cast<EventRec*>(p.events);
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(stream_base);
         attr[0].val.accessPolicyWindow.num_bytes = win;
         attr[0].val.accessPolicyWindow.hitRatio = float(std::min(1.0, double(plan->l2_persist_bytes) / double(win)));
         attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -261,19 +264,31 @@ template <int MODE>
 int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p, const LaunchShape& s, cudaStream_t stream) {
     if (p.n <= 0) return MCDP_OK;
     if constexpr (MODE == kModeReduced) {
+        // event + precedence record streams (mcdp_sweep.cuh)
+        const size_t bytes = size_t(plan->host.E) * sizeof(EventRec) + size_t(plan->host.P) * sizeof(PredRec);
         if (s.batches > 1)
-            return s.smem_tables ? launch_kernel(plan, sweep_kernel<MODE, true, true>, p, s, stream)
-                                 : launch_kernel(plan, sweep_kernel<MODE, false, true>, p, s, stream);
+            return s.smem_tables ? launch_kernel(plan, sweep_kernel<MODE, true, true>, p, s, s.smem, p.events, bytes, stream)
+                                 : launch_kernel(plan, sweep_kernel<MODE, false, true>, p, s, s.smem, p.events, bytes, stream);
+        return s.smem_tables ? launch_kernel(plan, sweep_kernel<MODE, true, false>, p, s, s.smem, p.events, bytes, stream)
+                             : launch_kernel(plan, sweep_kernel<MODE, false, false>, p, s, s.smem, p.events, bytes, stream);
+    } else {
+        // chunk stream (mcdp_chunk_sweep.cuh): tables (128-byte rounded) + per-warp chunk ring
+        const size_t bytes = size_t(plan->host.n_chunks) * size_t(kChunkBytes);
+        const size_t smem = ((s.smem + 127) & ~size_t(127)) + chunk_ring_bytes(s.threads / 32);
+        if (s.wpg > 1)
+            return s.smem_tables ? launch_kernel(plan, chunk_sweep_kernel<MODE, true, true>, p, s, smem, p.chunks, bytes, stream)
+                                 : launch_kernel(plan, chunk_sweep_kernel<MODE, false, true>, p, s, smem, p.chunks, bytes, stream);
+        return s.smem_tables ? launch_kernel(plan, chunk_sweep_kernel<MODE, true, false>, p, s, smem, p.chunks, bytes, stream)
+                             : launch_kernel(plan, chunk_sweep_kernel<MODE, false, false>, p, s, smem, p.chunks, bytes, stream);
     }
-    return s.smem_tables ? launch_kernel(plan, sweep_kernel<MODE, true, false>, p, s, stream)
-                         : launch_kernel(plan, sweep_kernel<MODE, false, false>, p, s, stream);
 }
 
 SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, int64_t ld) {
     SweepParams p{};
     const HostPlan& h = plan->host;
-    p.events = plan->d_events.p;
-    p.preds = plan->d_preds.p;
+    p.chunks = plan->d_chunks.p;
+    p.chunk_level_begin = plan->d_chunk_level_begin.p;
+    p.n_chunks = h.n_chunks;
     p.level_begin = plan->d_level_begin.p;
     p.orphans = plan->d_orphans.p;
     p.dists = plan->d_dists.p;
@@ -425,7 +440,7 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
         plan->smem_optin = prop.sharedMemPerBlockOptin;
         plan->l2_window_max = size_t(std::max(prop.accessPolicyMaxWindowSize, 0));
         // set aside L2 for the record stream (device-wide limit; the last plan created decides)
-        const size_t stream_bytes = plan->host.events.size() * sizeof(EventRec) + plan->host.preds.size() * sizeof(PredRec);
+        const size_t stream_bytes = plan->host.units.size() * sizeof(ChunkUnit);
         const size_t want = std::min<size_t>({stream_bytes + (stream_bytes >> 3) + (1u << 20),
                                              size_t(std::max(prop.persistingL2CacheMaxSize, 0)), size_t(64) << 20});
         if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
@@ -434,7 +449,8 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
             cudaGetLastError();
     }
     const HostPlan& h = plan->host;
-    int32_t rc = upload_stream(plan->d_stream, h.events, h.preds, &plan->d_events.p, &plan->d_preds.p);
+    int32_t rc = upload(plan->d_chunks, h.units);
+    if (!rc) rc = upload(plan->d_chunk_level_begin, h.chunk_level_begin);
     if (!rc) rc = upload(plan->d_level_begin, h.level_begin);
     if (!rc) rc = upload(plan->d_orphans, h.orphans);
     if (!rc) rc = upload(plan->d_dists, h.dists);

@@ -75,9 +75,10 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                 r.p[6] = a1 * p1;
                 r.flags = p0 < 1.0 ? 1 : 0;
                 {
-                    // 2 * shape in {1..8}: sum of floor(shape) exponentials (+ half a squared normal) is exact
+                    // 2 * shape in {1..6, 8}: sum of floor(shape) exponentials (+ half a squared normal) is exact
+                    // and needs at most the four 32-bit words of one Philox block
                     const double twice = 2.0 * p0;
-                    if (twice == std::floor(twice) && twice >= 1.0 && twice <= 8.0) {
+                    if (twice == std::floor(twice) && twice >= 1.0 && twice <= 8.0 && twice != 7.0) {
                         r.flags |= 8;
                         r.pad0 = int32_t(std::floor(p0));
                         r.pad1 = int32_t(twice) & 1;
@@ -187,6 +188,112 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
         out.dist_types.push_back(type);
     }
     return true;
+}
+
+
+// Gather-prefetch links of a chunk stream: every entry unit names the source row of the next
+// entry unit its warp will process (the next event of the chunk and continuation chunks
+// included); the chunk-opening header names the first entry's.
+void link_chunk_gathers(std::vector<ChunkUnit>& units) {
+    constexpr size_t U = size_t(kChunkUnits);
+    auto kind_of = [](const ChunkUnit& u) { return u.pred.meta >> 29; };
+    const size_t n_chunks = units.size() / U;
+    for (size_t c = 0; c < n_chunks; ++c) {
+        ChunkUnit* ch = &units[c * U];
+        const bool cont_in = kind_of(ch[0]) == kKindEnd;  // continuation header: the previous chunk links into this one
+        int last_pred = -1;
+        for (size_t u = 0; u < U; ++u) {
+            const uint32_t k = kind_of(ch[u]);
+            if (u > 0 && k == kKindEnd) break;
+            if (k >= kKindEvent) continue;
+            if (last_pred < 0) {
+                if (cont_in) {
+                    // last entry unit of the previous chunk (always unit U-1 of a full chunk)
+                    units[c * U - 1].pred.next_src_row = ch[u].pred.src_row;
+                } else {
+                    ch[0].head.first_src_row = ch[u].pred.src_row;
+                }
+            } else {
+                ch[last_pred].pred.next_src_row = ch[u].pred.src_row;
+            }
+            ch[u].pred.next_src_row = kNoRow;
+            last_pred = int(u);
+        }
+    }
+}
+
+// Packs the evaluation-ordered records into the chunk stream of mcdp_records.h.  Within a level
+// the chunks shrink towards the end (guided self-scheduling: a chunk takes about 1/32 of the units
+// still to go, at least 6), so that the warps which split a level reach its barrier within an
+// event or two of each other while most of the level is still handed out as full 512-byte chunks.
+void build_chunk_stream(HostPlan& out) {
+    out.units.clear();
+    out.chunk_level_begin.assign(size_t(out.n_levels) + 1, 0);
+    constexpr uint32_t U = uint32_t(kChunkUnits);
+    auto end_unit = [] {
+        ChunkUnit u{};
+        u.head.meta = kKindEnd << 29;
+        u.head.first_src_row = kNoRow;
+        return u;
+    };
+    auto header = [&](const EventRec& ev, bool cont, uint32_t remaining) {
+        ChunkUnit u{};
+        u.head.row = ev.row;
+        u.head.event = ev.event;
+        u.head.earliest = ev.earliest;
+        u.head.meta = cont ? ((kKindEnd << 29) | 1u) : (kKindEvent << 29);
+        u.head.remaining = remaining;
+        u.head.first_src_row = kNoRow;
+        return u;
+    };
+    auto pad_chunk = [&] {
+        while (out.units.size() % U) out.units.push_back(end_unit());
+    };
+    for (int32_t l = 0; l < out.n_levels; ++l) {
+        const int32_t pb = out.level_begin[l], pe = out.level_begin[size_t(l) + 1];
+        int64_t units_left = 0;
+        for (int32_t p = pb; p < pe; ++p) units_left += 1 + int64_t(out.events[p].fan_in);
+        uint32_t pos = 0;        // units used in the open chunk
+        uint32_t budget = U;     // units the open chunk may take
+        for (int32_t p = pb; p < pe; ++p) {
+            const EventRec& ev = out.events[p];
+            const uint32_t need = 1u + ev.fan_in;
+            if (need > U) {  // long event: own run of chunks, 15 entries each
+                pad_chunk();
+                const uint32_t per = U - 1u;
+                const uint32_t n_ch = (ev.fan_in + per - 1u) / per;
+                for (uint32_t j = 0; j < n_ch; ++j) {
+                    out.units.push_back(header(ev, j > 0, n_ch - 1u - j));
+                    for (uint32_t k = j * per; k < std::min(ev.fan_in, (j + 1u) * per); ++k) {
+                        ChunkUnit u{};
+                        u.pred = out.preds[ev.pred_begin + k];
+                        out.units.push_back(u);
+                    }
+                }
+                pad_chunk();
+                pos = 0;
+            } else {
+                if (pos > 0 && pos + need > budget) {
+                    pad_chunk();
+                    pos = 0;
+                }
+                if (pos == 0) budget = uint32_t(std::min<int64_t>(U, std::max<int64_t>(6, units_left / 32)));
+                out.units.push_back(header(ev, false, 0));
+                for (uint32_t k = 0; k < ev.fan_in; ++k) {
+                    ChunkUnit u{};
+                    u.pred = out.preds[ev.pred_begin + k];
+                    out.units.push_back(u);
+                }
+                pos += need;
+                if (pos >= U) pos = 0;  // exactly full
+            }
+            units_left -= need;
+        }
+        pad_chunk();
+        out.chunk_level_begin[size_t(l) + 1] = int32_t(out.units.size() / U);
+    }
+    out.n_chunks = int32_t(out.units.size() / U);
+    link_chunk_gathers(out.units);
 }
 
 }  // namespace
@@ -404,6 +511,8 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
         fill_dist(pr, act_dist[a]);
         out.orphans.push_back(pr);
     }
+
+    build_chunk_stream(out);
 
     // reduced-mode scratch slots: a slot is released once the LEVEL of the value's last consumer
     // has completed, so warps that split a level never race on a recycled row.

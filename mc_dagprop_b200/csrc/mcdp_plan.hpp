@@ -24,6 +24,11 @@ struct HostPlan {
     std::vector<int32_t> level_begin;  // [n_levels + 1] positions into events
     std::vector<PredRec> orphans;      // activities no precedence entry references (src fields unused)
 
+    // chunk stream of the full / injected sweep (rows = event ids), see mcdp_records.h
+    std::vector<ChunkUnit> units;           // n_chunks * kChunkUnits
+    std::vector<int32_t> chunk_level_begin;  // [n_levels + 1] positions into chunks
+    int32_t n_chunks = 0;
+
     // distributions
     std::vector<DistRec> dists;
     std::vector<int32_t> dist_types;   // activity_type of dists[i]

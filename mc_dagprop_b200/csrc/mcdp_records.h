@@ -31,7 +31,7 @@ static_assert(sizeof(EventRec) == 32, "EventRec must be 32 bytes");
 // One precedence entry (src event --activity--> this event), in the caller's order.  Everything the
 // sampler needs to dispatch is in the record itself (`meta`, `tab_off`), so the kind switch and the
 // table lookup do not wait on a dependent DistRec load.
-//   meta = kind << 29 | guide_log2 << 24 | scan << 23 | table_len      (kind 7 = no distribution;
+//   meta = kind << 29 | guide_log2 << 24 | scan << 23 | table_len      (kind 5 = no distribution;
 //          scan = 1 when a guide bucket may hold more than one cumulative boundary)
 //   table block in the pool: [guide: 2^g u32][cp: len f64][values: len f64]; for table kinds
 //   `tab_off` is the BYTE offset of the guide and `dist` the BYTE offset of cp (values follow cp)
@@ -46,7 +46,10 @@ struct alignas(16) PredRec {
 };
 static_assert(sizeof(PredRec) == 32, "PredRec must be 32 bytes");
 
-constexpr uint32_t kKindNone = 7u;
+constexpr uint32_t kKindNone = 5u;   // precedence entry without a distribution (duration = base)
+constexpr uint32_t kKindEvent = 6u;  // chunk stream: event header unit
+constexpr uint32_t kKindEnd = 7u;    // chunk stream: end of chunk (meta bit0 set: continuation header)
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 __host__ __device__ inline uint32_t pack_meta(uint32_t kind, uint32_t guide_log2, uint32_t len, uint32_t scan = 0) {
     return (kind << 29) | (guide_log2 << 24) | (scan << 23) | (len & 0x7FFFFFu);
 }
@@ -54,6 +57,34 @@ __host__ __device__ inline uint32_t guide_doubles(uint32_t guide_log2) {
     const uint32_t g = 1u << guide_log2;
     return g >= 2u ? g / 2u : 1u;
 }
+
+// ---- chunk stream (full / injected sweep) -------------------------------------------------------
+// The evaluation-ordered stream the sweep kernel consumes: 32-byte units grouped into 512-byte
+// chunks (kChunkUnits units).  A chunk is the unit of work a warp pulls (one bulk copy into its
+// shared-memory ring, cp.async.bulk + mbarrier) and never straddles a topological level:
+//     [EVENT header][its precedence entries ...][EVENT header][...] ... [END]
+// An event whose 1 + fan_in units do not fit starts a fresh chunk and continues through
+// `remaining` continuation chunks ([CONT header][entries ...]) that the same warp processes; a
+// warp that is handed a continuation chunk by the level cursor skips it.
+// Precedence-entry units are PredRec as is; `next_src_row` names the source row of the next entry
+// unit the same warp will process (next event of the chunk included), kNoRow when there is none.
+constexpr int kChunkUnits = 16;
+constexpr int kChunkBytes = kChunkUnits * 32;
+struct alignas(16) HeaderUnit {
+    uint32_t row;            // realized / cause row of the event
+    uint32_t event;          // event id
+    double earliest;
+    uint32_t meta;           // kKindEvent << 29, or kKindEnd << 29 | 1 for a continuation header
+    uint32_t remaining;      // continuation chunks that still follow this chunk's last event
+    uint32_t first_src_row;  // chunk-opening header: source row of the chunk's first entry (else kNoRow)
+    uint32_t pad;
+};
+static_assert(sizeof(HeaderUnit) == 32, "HeaderUnit must be 32 bytes");
+union ChunkUnit {
+    PredRec pred;
+    HeaderUnit head;
+};
+static_assert(sizeof(ChunkUnit) == 32, "ChunkUnit must be 32 bytes");
 
 // Distribution parameters, one per activity_type.
 //   CONSTANT     p0 = factor
@@ -68,7 +99,7 @@ struct alignas(16) DistRec {
     int32_t tab_off;
     int32_t guide_log2;
     int32_t flags;      // bit0 gamma shape < 1, bit1 exponential series, bit2 table needs the scan loop,
-                        // bit3 gamma with 2*shape in 1..8 (exact transformation: pad0 = floor(shape), pad1 = half term)
+                        // bit3 gamma with 2*shape in {1..6, 8} (exact transformation: pad0 = floor(shape), pad1 = half term)
     int32_t pad0, pad1, pad2;
     double p[8];
 };

@@ -205,7 +205,7 @@ __device__ __forceinline__ void gamma_variate2(const DistRec& d, uint32_t seed_a
     }
 }
 
-// Gamma with 2 * shape in {1, ..., 8}: exact transformation without rejection.
+// Gamma with 2 * shape in {1, ..., 6, 8}: exact transformation without rejection.
 //   Gamma(k + h/2, scale) = scale * ( -ln(u_1 ... u_k)  +  h * (-ln u') cos^2(2 pi u'') ),   k = floor(shape), h in {0,1}
 // (a sum of k unit exponentials plus, for half-integer shapes, half the square of a Box-Muller
 // normal).  The logs are fp64 (log_pos), cos is the fp32 hardware approximation.  Up to two 32-bit

@@ -30,6 +30,8 @@ struct SweepParams {
     const EventRec* events;
     const PredRec* preds;
     const int32_t* level_begin;
+    const ChunkUnit* chunks;             // chunk stream (full / injected modes, mcdp_chunk_sweep.cuh)
+    const int32_t* chunk_level_begin;    // [n_levels + 1] positions into chunks
     const PredRec* orphans;
     const DistRec* dists;
     const double* tab_pool;
@@ -47,7 +49,7 @@ struct SweepParams {
     double max_delay;
     int64_t n, ld;
     int32_t n_levels, n_orphans, n_dists, tab_pool_len;
-    int32_t n_thresholds, n_bins, E;
+    int32_t n_thresholds, n_bins, E, n_chunks;
     uint32_t last_pred;  // index of the last precedence record (prefetch clamp)
     int32_t seed0;
     PhiloxKeys keys;  // round keys of Philox key word 0 (stream_key + r * 0x9E3779B9)

@@ -526,8 +526,8 @@ static double spec_sample_extra(const or_dist* d, double base, uint32_t act, uin
             const uint32_t key[2] = {stream_key, SPEC_KEY1};
             double x = 0.0;
             const double twice = 2.0 * d->p0;
-            if (twice == floor(twice) && twice >= 1.0 && twice <= 8.0) {
-                /* exact transformation for 2*shape in 1..8: k = floor(shape) unit exponentials (+ half a squared
+            if (twice == floor(twice) && twice >= 1.0 && twice <= 8.0 && twice != 7.0) {
+                /* exact transformation for 2*shape in {1..6, 8}: k = floor(shape) unit exponentials (+ half a squared
                  * Box-Muller normal); <= 2 uniforms: the seed's half of block (seed>>1, act, j, 'ERLG'), else the
                  * four words of block (seed, act, j, 'ERLG'); draw j+1 when x > max_scale */
                 const int k = (int)floor(d->p0), half = ((int)twice) & 1;

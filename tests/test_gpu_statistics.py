@@ -36,10 +36,11 @@ CASES = {
     "gamma_shape_half": lambda d: d.add_gamma(1, 0.5, 0.3, 5.0),
     "gamma_shape_7_untruncated": lambda d: d.add_gamma(1, 7.3, 0.2),
     "gamma_truncated": lambda d: d.add_gamma(1, 2.0, 1.0, 1.5),
-    # 2 * shape in 1..8 takes the exact-transformation path (sum of exponentials + half a squared normal) ...
+    # 2 * shape in {1..6, 8} takes the exact-transformation path (sum of exponentials + half a squared normal) ...
     "gamma_shape_1": lambda d: d.add_gamma(1, 1.0, 0.4, 6.0),
     "gamma_shape_1p5": lambda d: d.add_gamma(1, 1.5, 0.4, 6.0),
-    "gamma_shape_3p5_truncated": lambda d: d.add_gamma(1, 3.5, 0.5, 2.0),
+    "gamma_shape_2p5_truncated": lambda d: d.add_gamma(1, 2.5, 0.5, 1.5),
+    "gamma_shape_3p5_truncated": lambda d: d.add_gamma(1, 3.5, 0.5, 2.0),  # five uniforms: Marsaglia-Tsang
     "gamma_shape_4": lambda d: d.add_gamma(1, 4.0, 0.25),
     # ... every other shape Marsaglia-Tsang
     "gamma_shape_2p3": lambda d: d.add_gamma(1, 2.3, 0.1, 5.0),
