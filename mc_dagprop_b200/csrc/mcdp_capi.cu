@@ -113,6 +113,7 @@ struct mcdp_plan {
     DevBuf<PredRec> d_orphans;
     DevBuf<DistRec> d_dists;
     DevBuf<double> d_tab;
+    DevBuf<double> d_log_tab;
     // reduced-mode variant of the stream (rows = recycled scratch slots), built on first use
     DevBuf<double> d_scratch;
     bool red_ready = false;
@@ -140,6 +141,7 @@ struct mcdp_plan {
         d_orphans.release();
         d_dists.release();
         d_tab.release();
+        d_log_tab.release();
         d_scratch.release();
         d_acts.release();
         d_norm_cache.release();
@@ -226,7 +228,7 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false,
     const size_t need = sizeof(DistRec) * h.dists.size() + sizeof(double) * h.tab_pool.size();
     // keep several CTAs per SM resident: stage only when the tables are a modest share of shared memory
     s.smem_tables = need > 0 && need <= std::min<size_t>(plan->smem_optin, 64 * 1024);
-    s.smem = s.smem_tables ? need : 0;
+    s.smem = size_t(kLogTabBytes) + (s.smem_tables ? need : 0);  // the log table of mcdp_math.cuh is always staged
     if (reduced && n_bins > 0 && batches > 1) s.smem = ((s.smem + 15) & ~size_t(15)) + size_t(wpg * gpc) * size_t(n_bins) * 4;
     return s;
 }
@@ -293,6 +295,7 @@ SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, 
     p.orphans = plan->d_orphans.p;
     p.dists = plan->d_dists.p;
     p.tab_pool = plan->d_tab.p;
+    p.log_tab = plan->d_log_tab.p;
     p.n = n;
     p.ld = ld;
     p.n_levels = h.n_levels;
@@ -455,6 +458,11 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
     if (!rc) rc = upload(plan->d_orphans, h.orphans);
     if (!rc) rc = upload(plan->d_dists, h.dists);
     if (!rc) rc = upload(plan->d_tab, h.tab_pool);
+    if (!rc) {
+        std::vector<double> lt(size_t(2 * kLogTabEntries));
+        make_log_table(lt.data());
+        rc = upload(plan->d_log_tab, lt);
+    }
     if (rc) {
         delete plan;
         return rc;

@@ -68,18 +68,22 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     const DistRec* dists = p.dists;
     const double* tab = p.tab_pool;
-    size_t smem_used = 0;
+    // the log table of mcdp_math.cuh opens the dynamic shared memory
+    for (int i = threadIdx.x; i < kLogTabEntries; i += blockDim.x)
+        reinterpret_cast<int4*>(smem_dyn)[i] = __ldg(reinterpret_cast<const int4*>(p.log_tab) + i);
+    const uint32_t log_tab = uint32_t(__cvta_generic_to_shared(smem_dyn));
+    size_t smem_used = kLogTabBytes;
     if constexpr (SMEM) {
         // stage distribution records + guide / inverse-CDF tables once per CTA
-        DistRec* s_dists = reinterpret_cast<DistRec*>(smem_dyn);
-        double* s_tab = reinterpret_cast<double*>(smem_dyn + sizeof(DistRec) * p.n_dists);
+        DistRec* s_dists = reinterpret_cast<DistRec*>(smem_dyn + kLogTabBytes);
+        double* s_tab = reinterpret_cast<double*>(smem_dyn + kLogTabBytes + sizeof(DistRec) * p.n_dists);
         const int n16 = int(sizeof(DistRec) / 16) * p.n_dists;
         for (int i = threadIdx.x; i < n16; i += blockDim.x)
             reinterpret_cast<int4*>(s_dists)[i] = __ldg(reinterpret_cast<const int4*>(p.dists) + i);
         for (int i = threadIdx.x; i < p.tab_pool_len; i += blockDim.x) s_tab[i] = __ldg(p.tab_pool + i);
         dists = s_dists;
         tab = s_tab;
-        smem_used = (sizeof(DistRec) * p.n_dists + sizeof(double) * p.tab_pool_len + 127) & ~size_t(127);
+        smem_used = (kLogTabBytes + sizeof(DistRec) * p.n_dists + sizeof(double) * p.tab_pool_len + 127) & ~size_t(127);
     }
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
                 } else {
                     double ea, eb;
                     sample_extra2<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, seed_a, seed_b, paired,
-                                        key0, ea, eb);
+                                        key0, log_tab, ea, eb);
                     da = __dadd_rn(base, ea);  // _core.cpp:328
                     db = __dadd_rn(base, eb);
                 }
@@ -267,7 +271,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
             if ((meta >> 29) != kKindNone) {
                 double ea, eb;
                 sample_extra2<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, seed_a, seed_b, paired, key0,
-                                    ea, eb);
+                                    log_tab, ea, eb);
                 da = __dadd_rn(base, ea);
                 db = __dadd_rn(base, eb);
             }

@@ -214,68 +214,78 @@ __device__ __forceinline__ void gamma_variate2(const DistRec& d, uint32_t seed_a
 // _core.cpp:98-104).
 constexpr uint32_t kTagErlang = 0x45524C47u;  // 'ERLG'
 
-__device__ __forceinline__ double erlang_value(const DistRec& d, int k, bool half, uint32_t w0, uint32_t w1, uint32_t w2,
-                                               uint32_t w3) {
-    // words are consumed in order: k product uniforms, then (u', u'') of the half term
-    double e = 0.0;
-    if (k > 0) {
-        double prod = uniform32(w0);
-        if (k > 1) prod *= uniform32(w1);
-        if (k > 2) prod *= uniform32(w2);
-        if (k > 3) prod *= uniform32(w3);
-        e = -log_pos(prod);
-    }
-    if (half) {
-        const uint32_t wu = k == 0 ? w0 : (k == 1 ? w1 : w2);
-        const uint32_t wa = k == 0 ? w1 : (k == 1 ? w2 : w3);
-        const float c = cos_approx(float(int(wa)) * 1.4629180792671596e-9f);  // cos(2 pi * int32 / 2^32)
-        e = fma(-log_pos(uniform32(wu)), double(c * c), e);
+__device__ __forceinline__ double half_term(uint32_t wu, uint32_t wa, uint32_t log_tab) {
+    const float c = cos_approx(float(int(wa)) * 1.4629180792671596e-9f);  // cos(2 pi * int32 / 2^32)
+    return -log_pos(uniform32(wu), log_tab) * double(c * c);
+}
+// words are consumed in order: k product uniforms, then (u', u'') of the half term.  `variant` = 2 * k + h
+// (warp-uniform): one straight-line case per supported shape.
+__device__ __forceinline__ double erlang_value(const DistRec& d, int variant, uint32_t w0, uint32_t w1, uint32_t w2,
+                                               uint32_t w3, uint32_t log_tab) {
+    double e;
+    switch (variant) {
+        case 1: e = half_term(w0, w1, log_tab); break;                                                   // shape 1/2
+        case 2: e = -log_pos(uniform32(w0), log_tab); break;                                             // 1
+        case 3: e = half_term(w1, w2, log_tab) - log_pos(uniform32(w0), log_tab); break;                 // 3/2
+        case 4: e = -log_pos(uniform32(w0) * uniform32(w1), log_tab); break;                             // 2
+        case 5: e = half_term(w2, w3, log_tab) - log_pos(uniform32(w0) * uniform32(w1), log_tab); break;  // 5/2
+        case 6: e = -log_pos(uniform32(w0) * uniform32(w1) * uniform32(w2), log_tab); break;             // 3
+        default: e = -log_pos((uniform32(w0) * uniform32(w1)) * (uniform32(w2) * uniform32(w3)), log_tab); break;  // 4
     }
     return d.p[1] * e;
 }
 
-__device__ __forceinline__ void erlang_variate2(const DistRec& d, uint32_t seed_a, uint32_t seed_b, bool paired,
-                                                uint32_t act, const PhiloxKeys& key0, double& xa, double& xb) {
-    const int k = d.pad0;
-    const bool half = d.pad1 != 0;
-    const bool shared_block = k + 2 * int(half) <= 2;  // <= 64 bits per sample
-    const double mx = d.p[2];
-    uint32_t ja = 0u, jb = 0u;
-    bool need_a = true, need_b = true;
-    for (;;) {
-        double ya, yb;
-        if (shared_block) {
-            if (paired && ja == jb) {
-                const Philox4 r = philox4x32_10(seed_a >> 1, act, ja, kTagErlang, key0);
-                ya = erlang_value(d, k, half, r.x, r.y, 0u, 0u);
-                yb = erlang_value(d, k, half, r.z, r.w, 0u, 0u);
-            } else {
-                const Philox4 ra = philox4x32_10(seed_a >> 1, act, ja, kTagErlang, key0);
-                const Philox4 rb = philox4x32_10(seed_b >> 1, act, jb, kTagErlang, key0);
-                const bool oa = seed_a & 1u, ob = seed_b & 1u;
-                ya = erlang_value(d, k, half, oa ? ra.z : ra.x, oa ? ra.w : ra.y, 0u, 0u);
-                yb = erlang_value(d, k, half, ob ? rb.z : rb.x, ob ? rb.w : rb.y, 0u, 0u);
-            }
+// draw j of both samples; one Philox block serves the seed pair when a sample needs <= 2 words
+__device__ __forceinline__ void erlang_draw2(const DistRec& d, int variant, uint32_t seed_a, uint32_t seed_b, bool paired,
+                                             uint32_t act, uint32_t ja, uint32_t jb, const PhiloxKeys& key0,
+                                             uint32_t log_tab, double& ya, double& yb) {
+    if (variant <= 2 || variant == 4) {  // <= 64 bits per sample
+        if (paired && ja == jb) {
+            const Philox4 r = philox4x32_10(seed_a >> 1, act, ja, kTagErlang, key0);
+            ya = erlang_value(d, variant, r.x, r.y, 0u, 0u, log_tab);
+            yb = erlang_value(d, variant, r.z, r.w, 0u, 0u, log_tab);
         } else {
-            const Philox4 ra = philox4x32_10(seed_a, act, ja, kTagErlang, key0);
-            const Philox4 rb = philox4x32_10(seed_b, act, jb, kTagErlang, key0);
-            ya = erlang_value(d, k, half, ra.x, ra.y, ra.z, ra.w);
-            yb = erlang_value(d, k, half, rb.x, rb.y, rb.z, rb.w);
+            const Philox4 ra = philox4x32_10(seed_a >> 1, act, ja, kTagErlang, key0);
+            const Philox4 rb = philox4x32_10(seed_b >> 1, act, jb, kTagErlang, key0);
+            const bool oa = seed_a & 1u, ob = seed_b & 1u;
+            ya = erlang_value(d, variant, oa ? ra.z : ra.x, oa ? ra.w : ra.y, 0u, 0u, log_tab);
+            yb = erlang_value(d, variant, ob ? rb.z : rb.x, ob ? rb.w : rb.y, 0u, 0u, log_tab);
         }
-        if (need_a) {
-            xa = ya;
-            need_a = ya > mx && ja + 1u < kGammaMaxAttempts;
-            ja += need_a ? 1u : 0u;
-        }
-        if (need_b) {
-            xb = yb;
-            need_b = yb > mx && jb + 1u < kGammaMaxAttempts;
-            jb += need_b ? 1u : 0u;
-        }
-        if (!__any_sync(0xFFFFFFFFu, need_a || need_b)) break;
+    } else {
+        const Philox4 ra = philox4x32_10(seed_a, act, ja, kTagErlang, key0);
+        const Philox4 rb = philox4x32_10(seed_b, act, jb, kTagErlang, key0);
+        ya = erlang_value(d, variant, ra.x, ra.y, ra.z, ra.w, log_tab);
+        yb = erlang_value(d, variant, rb.x, rb.y, rb.z, rb.w, log_tab);
     }
-    xa = xa > mx ? mx : xa;  // only after the attempt cap
-    xb = xb > mx ? mx : xb;
+}
+
+__device__ __forceinline__ void erlang_variate2(const DistRec& d, uint32_t seed_a, uint32_t seed_b, bool paired,
+                                                uint32_t act, const PhiloxKeys& key0, uint32_t log_tab, double& xa,
+                                                double& xb) {
+    const int variant = 2 * d.pad0 + d.pad1;
+    const double mx = d.p[2];
+    erlang_draw2(d, variant, seed_a, seed_b, paired, act, 0u, 0u, key0, log_tab, xa, xb);
+    // truncation (_core.cpp:98-104): draws 1, 2, ... until x <= max_scale; rare, so off the straight path
+    bool need_a = xa > mx, need_b = xb > mx;
+    if (__any_sync(0xFFFFFFFFu, need_a || need_b)) {
+        uint32_t ja = 0u, jb = 0u;
+        do {
+            ja += need_a ? 1u : 0u;
+            jb += need_b ? 1u : 0u;
+            double ya, yb;
+            erlang_draw2(d, variant, seed_a, seed_b, paired, act, ja, jb, key0, log_tab, ya, yb);
+            if (need_a) {
+                xa = ya;
+                need_a = ya > mx && ja + 1u < kGammaMaxAttempts;
+            }
+            if (need_b) {
+                xb = yb;
+                need_b = yb > mx && jb + 1u < kGammaMaxAttempts;
+            }
+        } while (__any_sync(0xFFFFFFFFu, need_a || need_b));
+        xa = xa > mx ? mx : xa;  // only after the attempt cap
+        xb = xb > mx ? mx : xb;
+    }
 }
 
 // Extra delays of one activity for the two samples a thread owns.  `meta`/`tab_off` come from the
@@ -285,8 +295,8 @@ __device__ __forceinline__ void erlang_variate2(const DistRec& d, uint32_t seed_
 template <bool SMEM>
 __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, const DistRec* dists, uint32_t dist,
                                               const double* tab, double base, uint32_t act, uint32_t seed_a,
-                                              uint32_t seed_b, bool paired, const PhiloxKeys& key0, double& ea,
-                                              double& eb) {
+                                              uint32_t seed_b, bool paired, const PhiloxKeys& key0, uint32_t log_tab,
+                                              double& ea, double& eb) {
     const uint32_t kind = meta >> 29;
     if (kind == MCDP_DIST_CONSTANT) {
         ea = eb = __dmul_rn(base, dists[dist].p[0]);  // _core.cpp:75
@@ -295,7 +305,7 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, c
     if (kind == MCDP_DIST_GAMMA) {
         double xa, xb;
         if (dists[dist].flags & 8)
-            erlang_variate2(dists[dist], seed_a, seed_b, paired, act, key0, xa, xb);
+            erlang_variate2(dists[dist], seed_a, seed_b, paired, act, key0, log_tab, xa, xb);
         else
             gamma_variate2(dists[dist], seed_a, seed_b, act, key0, xa, xb);
         ea = __dmul_rn(xa, base);
@@ -327,11 +337,11 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, c
         const double lam = d.p[0], mx = d.p[1], F = d.p[2];
         double xa, xb;
         if (d.flags & 2) {  // F < 2^-10: series keeps the relative accuracy (both samples in one block)
-            xa = lam * neg_log1m(ua * F, true);
-            xb = lam * neg_log1m(ub * F, true);
+            xa = lam * neg_log1m(ua * F, true, log_tab);
+            xb = lam * neg_log1m(ub * F, true, log_tab);
         } else {
-            xa = lam * neg_log1m(ua * F, false);
-            xb = lam * neg_log1m(ub * F, false);
+            xa = lam * neg_log1m(ua * F, false, log_tab);
+            xb = lam * neg_log1m(ub * F, false, log_tab);
         }
         xa = xa > mx ? mx : xa;
         xb = xb > mx ? mx : xb;

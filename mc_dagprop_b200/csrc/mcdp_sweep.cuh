@@ -35,6 +35,7 @@ struct SweepParams {
     const PredRec* orphans;
     const DistRec* dists;
     const double* tab_pool;
+    const double* log_tab;  // {rc, lc} pairs of mcdp_math.cuh (kLogTabEntries)
     const int32_t* seeds;  // nullptr => seed0 + sample index
     double* realized;      // [rows][ld]  (output in full/injected mode, scratch in reduced mode)
     double* durations;     // [A][ld]     full mode: written
@@ -78,18 +79,22 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const DistRec* dists = p.dists;
     const double* tab = p.tab_pool;
-    size_t smem_used = 0;
+    // the log table of mcdp_math.cuh opens the dynamic shared memory
+    for (int i = threadIdx.x; i < kLogTabEntries; i += blockDim.x)
+        reinterpret_cast<int4*>(smem_raw)[i] = __ldg(reinterpret_cast<const int4*>(p.log_tab) + i);
+    const uint32_t log_tab = uint32_t(__cvta_generic_to_shared(smem_raw));
+    size_t smem_used = kLogTabBytes;
     if constexpr (SMEM) {
         // stage distribution records + guide / inverse-CDF tables once per CTA
-        DistRec* s_dists = reinterpret_cast<DistRec*>(smem_raw);
-        double* s_tab = reinterpret_cast<double*>(smem_raw + sizeof(DistRec) * p.n_dists);
+        DistRec* s_dists = reinterpret_cast<DistRec*>(smem_raw + kLogTabBytes);
+        double* s_tab = reinterpret_cast<double*>(smem_raw + kLogTabBytes + sizeof(DistRec) * p.n_dists);
         const int n16 = int(sizeof(DistRec) / 16) * p.n_dists;
         for (int i = threadIdx.x; i < n16; i += blockDim.x)
             reinterpret_cast<int4*>(s_dists)[i] = __ldg(reinterpret_cast<const int4*>(p.dists) + i);
         for (int i = threadIdx.x; i < p.tab_pool_len; i += blockDim.x) s_tab[i] = __ldg(p.tab_pool + i);
         dists = s_dists;
         tab = s_tab;
-        smem_used = sizeof(DistRec) * p.n_dists + sizeof(double) * p.tab_pool_len;
+        smem_used = kLogTabBytes + sizeof(DistRec) * p.n_dists + sizeof(double) * p.tab_pool_len;
     }
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
             w_hist = all + warp * p.n_bins;
         }
     }
-    if (SMEM || MODE == kModeReduced) __syncthreads();
+    __syncthreads();
 
     const int wpg = p.warps_per_group;
     const int group_in_cta = warp / wpg;
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
                 } else {
                     double ea, eb;
                     sample_extra2<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, seed_a, seed_b, paired,
-                                        key0, ea, eb);
+                                        key0, log_tab, ea, eb);
                     da = __dadd_rn(base, ea);  // _core.cpp:328
                     db = __dadd_rn(base, eb);
                 }
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kerne
             if ((meta >> 29) != kKindNone) {
                 double ea, eb;
                 sample_extra2<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, seed_a0, seed_b0, paired0,
-                                    key0, ea, eb);
+                                    key0, log_tab, ea, eb);
                 da = __dadd_rn(base, ea);
                 db = __dadd_rn(base, eb);
             }
