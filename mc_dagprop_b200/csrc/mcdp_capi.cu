@@ -298,6 +298,10 @@ SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, 
     p.log_tab = plan->d_log_tab.p;
     p.n = n;
     p.ld = ld;
+    p.ldb8 = uint32_t(ld) * 8u;
+    p.ldb4 = uint32_t(ld) * 4u;
+    p.smem_tab_off = uint32_t(kLogTabBytes + sizeof(DistRec) * h.dists.size());
+    p.smem_ring_off = uint32_t((s.smem + 127) & ~size_t(127));
     p.n_levels = h.n_levels;
     p.n_orphans = int32_t(h.orphans.size());
     p.n_dists = int32_t(h.dists.size());

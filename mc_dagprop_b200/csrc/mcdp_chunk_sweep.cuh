@@ -50,6 +50,7 @@ __device__ __forceinline__ int4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 // base + row * stride as ONE 32x32+64 multiply-add (the lane's column base stays in registers)
 __device__ __forceinline__ char* row_ptr(char* base, uint32_t row, uint32_t stride) {
     char* r;
@@ -66,30 +67,33 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
     chunk_sweep_kernel(const __grid_constant__ SweepParams p) {
     static_assert(MODE == kModeFull || MODE == kModeInjected, "reduced mode runs sweep_kernel");
     extern __shared__ __align__(128) unsigned char smem_dyn[];
-    const DistRec* dists = p.dists;
-    const double* tab = p.tab_pool;
-    // the log table of mcdp_math.cuh opens the dynamic shared memory
+    // Dynamic shared memory: [log table][DistRec[] + table pool (SMEM)][per-warp chunk rings].  Everything
+    // is addressed through ONE shared-window base register (kept opaque so that it is not re-derived
+    // from special registers at every use) plus offsets the host put into the parameter block.
+    uint32_t smem_base = smem_u32(smem_dyn);
+    asm volatile("" : "+r"(smem_base));
     for (int i = threadIdx.x; i < kLogTabEntries; i += blockDim.x)
         reinterpret_cast<int4*>(smem_dyn)[i] = __ldg(reinterpret_cast<const int4*>(p.log_tab) + i);
-    const uint32_t log_tab = uint32_t(__cvta_generic_to_shared(smem_dyn));
-    size_t smem_used = kLogTabBytes;
+    const uint32_t log_tab = smem_base;
+    typename Mem<SMEM>::ptr dists, tab;
     if constexpr (SMEM) {
         // stage distribution records + guide / inverse-CDF tables once per CTA
-        DistRec* s_dists = reinterpret_cast<DistRec*>(smem_dyn + kLogTabBytes);
-        double* s_tab = reinterpret_cast<double*>(smem_dyn + kLogTabBytes + sizeof(DistRec) * p.n_dists);
+        int4* s_dists = reinterpret_cast<int4*>(smem_dyn + kLogTabBytes);
+        double* s_tab = reinterpret_cast<double*>(smem_dyn + p.smem_tab_off);
         const int n16 = int(sizeof(DistRec) / 16) * p.n_dists;
-        for (int i = threadIdx.x; i < n16; i += blockDim.x)
-            reinterpret_cast<int4*>(s_dists)[i] = __ldg(reinterpret_cast<const int4*>(p.dists) + i);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) s_dists[i] = __ldg(reinterpret_cast<const int4*>(p.dists) + i);
         for (int i = threadIdx.x; i < p.tab_pool_len; i += blockDim.x) s_tab[i] = __ldg(p.tab_pool + i);
-        dists = s_dists;
-        tab = s_tab;
-        smem_used = (kLogTabBytes + sizeof(DistRec) * p.n_dists + sizeof(double) * p.tab_pool_len + 127) & ~size_t(127);
+        dists = smem_base + uint32_t(kLogTabBytes);
+        tab = smem_base + p.smem_tab_off;
+    } else {
+        dists = reinterpret_cast<const char*>(p.dists);
+        tab = reinterpret_cast<const char*>(p.tab_pool);
     }
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int n_warps = blockDim.x >> 5;
     // this warp's ring: two 512-byte chunk buffers followed by their two mbarriers
-    const uint32_t ring0 = smem_u32(smem_dyn + smem_used) + uint32_t(warp) * uint32_t(kRingStride);
+    const uint32_t ring0 = smem_base + p.smem_ring_off + uint32_t(warp) * uint32_t(kRingStride);
     const uint32_t bar0 = ring0 + 2u * uint32_t(kChunkBytes);
     if (lane == 0) {
         mbar_init(bar0, 1);
@@ -105,7 +109,6 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
     const int64_t batch0 = int64_t(blockIdx.x) * groups_per_cta + group_in_cta;
     if (batch0 * 64 >= p.n) return;  // whole group (all its warps) out of range
     const PhiloxKeys& key0 = p.keys;
-    const uint32_t ldb8 = uint32_t(p.ld) * 8u, ldb4 = uint32_t(p.ld) * 4u;
 
     // the lane's two sample columns (ld is a multiple of 64: both are in-bounds padding at worst)
     const int64_t s0 = batch0 * 64 + 2 * lane;
@@ -120,10 +123,16 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
         }
     }
     const bool paired = ((seed_a & 1u) == 0u) && (seed_b == seed_a + 1u);
-    char* const r_lane = reinterpret_cast<char*>(p.realized) + s0 * 8;
-    char* const d_lane = MODE == kModeFull ? reinterpret_cast<char*>(p.durations) + s0 * 8
-                                           : const_cast<char*>(reinterpret_cast<const char*>(p.inj)) + s0 * 8;
-    char* const c_lane = reinterpret_cast<char*>(p.cause) + s0 * 4;
+    // Row addressing: array base (uniform, from the parameter block) + row * ld * 8 + the lane's column
+    // offset, which fits 32 bits (ld < 2^29): one register of per-lane addressing state for all arrays.
+    const uint32_t lane_off = uint32_t(s0) * 8u;
+    auto f64_row = [&](const void* base, uint32_t row) -> char* {
+        return const_cast<char*>(reinterpret_cast<const char*>(base)) + (uint64_t(row) * p.ldb8 + lane_off);
+    };
+    auto i32_row = [&](const void* base, uint32_t row) -> char* {
+        return const_cast<char*>(reinterpret_cast<const char*>(base)) + (uint64_t(row) * p.ldb4 + (lane_off >> 1));
+    };
+    const void* const dur_base = MODE == kModeFull ? static_cast<const void*>(p.durations) : static_cast<const void*>(p.inj);
 
     // ---- chunk pipeline: the ring's buffers alternate; `phase` holds the mbarrier parity of each ----
     uint32_t buf_sel = 0u, phase = 0u;
@@ -160,8 +169,8 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
     double2 nrs = make_double2(0.0, 0.0);
     auto finalize = [&]() {
         // _core.cpp:348-349.  realized rows are gathered by other warps: L2 only (st.cg / ld.cg)
-        __stcg(reinterpret_cast<double2*>(row_ptr(r_lane, row, ldb8)), make_double2(ref_min(lat_a, ub), ref_min(lat_b, ub)));
-        __stcs(reinterpret_cast<int2*>(row_ptr(c_lane, row, ldb4)), make_int2(cause_a, cause_b));
+        __stcg(reinterpret_cast<double2*>(f64_row(p.realized, row)), make_double2(ref_min(lat_a, ub), ref_min(lat_b, ub)));
+        __stcs(reinterpret_cast<int2*>(i32_row(p.cause, row)), make_int2(cause_a, cause_b));
         open = false;
     };
     auto process = [&](uint32_t buf, int u0, uint32_t remaining) {
@@ -174,7 +183,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
             // the realized row of the NEXT entry unit is requested before this unit's delay is drawn
             // (q1.z: PredRec::next_src_row / HeaderUnit::first_src_row)
             const double2 rs = nrs;
-            if (uint32_t(q1.z) != kNoRow) nrs = __ldcg(reinterpret_cast<const double2*>(row_ptr(r_lane, uint32_t(q1.z), ldb8)));
+            if (uint32_t(q1.z) != kNoRow) nrs = __ldcg(reinterpret_cast<const double2*>(f64_row(p.realized, uint32_t(q1.z))));
             if (kind >= kKindEvent) {
                 if (open) finalize();
                 if (kind == kKindEnd) break;
@@ -192,7 +201,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
             double da, db;
             if constexpr (MODE == kModeInjected) {
                 double2 dd = make_double2(0.0, 0.0);
-                if (act != kNoAct) dd = __ldcs(reinterpret_cast<const double2*>(row_ptr(d_lane, act, ldb8)));
+                if (act != kNoAct) dd = __ldcs(reinterpret_cast<const double2*>(f64_row(dur_base, act)));
                 da = dd.x;
                 db = dd.y;
             } else {
@@ -205,7 +214,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
                     da = __dadd_rn(base, ea);  // _core.cpp:328
                     db = __dadd_rn(base, eb);
                 }
-                if (act != kNoAct) __stcs(reinterpret_cast<double2*>(row_ptr(d_lane, act, ldb8)), make_double2(da, db));
+                if (act != kNoAct) __stcs(reinterpret_cast<double2*>(f64_row(dur_base, act)), make_double2(da, db));
             }
             // _core.cpp:341-346
             const double ta = ref_min(__dadd_rn(rs.x, da), ub);
@@ -253,7 +262,21 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
                 if constexpr (!DYN) ++seq;
             }
             if (cn < le) issue(cn, buf_sel);
-            if (!skip) process(buf, is_cont ? 1 : 0, remaining);
+            if (!skip) {
+                // Pull the realized rows this chunk gathers towards L2 now (the gather proper runs only one
+                // unit ahead of its use).  Lane l covers the 128-byte line (l & 3) of this warp's 512-byte
+                // row segment for the entry units (l >> 2), 8 + (l >> 2), ...
+#pragma unroll
+                for (int h = 0; h < kChunkUnits / 8; ++h) {
+                    const uint32_t ua = buf + (uint32_t(lane >> 2) + 8u * uint32_t(h)) * 32u;
+                    uint32_t src, meta;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(src) : "r"(ua));
+                    asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(meta) : "r"(ua));
+                    if ((meta >> 29) < kKindEvent)
+                        prefetch_l2(f64_row(p.realized, src) - lane * 16 + (lane & 3) * 128);
+                }
+                process(buf, is_cont ? 1 : 0, remaining);
+            }
             __syncwarp();  // every lane is done with `buf` before a later bulk copy may overwrite it
             c = cn;
         }
@@ -275,7 +298,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
                 da = __dadd_rn(base, ea);
                 db = __dadd_rn(base, eb);
             }
-            __stcs(reinterpret_cast<double2*>(row_ptr(d_lane, act, ldb8)), make_double2(da, db));
+            __stcs(reinterpret_cast<double2*>(f64_row(dur_base, act)), make_double2(da, db));
         }
     }
 }

@@ -10,6 +10,7 @@
 //   PAIR    ctr = (seed >> 1, act, j, 'PAIR')          -- one block serves seeds {2k, 2k+1}: 64 bits each
 //   SOLO    ctr = (seed,      act, t, 'SOLO')          -- gamma attempt t: 4 x 32 bits
 #pragma once
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -72,39 +73,66 @@ __device__ __forceinline__ double uniform32(uint32_t w) {
     return __hiloint2double(0x41300000, static_cast<int>(w)) - (1048576.0 - 0x1p-33);
 }
 
-// Table access: SMEM => the pool pointer addresses shared memory (staged copy), else global (L1/L2).
+// Table / distribution-record access.  SMEM: the staged copy in shared memory, addressed by 32-bit
+// shared-window addresses and explicit ld.shared (no generic pointers: the kernel keeps ONE base
+// register instead of re-deriving the window base at every use); else global memory through L1/L2.
 template <bool SMEM>
-__device__ __forceinline__ double tab_ld(const double* p) {
-    if constexpr (SMEM) return *p;
-    else return __ldg(p);
-}
+struct Mem;
+template <>
+struct Mem<true> {
+    using ptr = uint32_t;
+    static __device__ __forceinline__ double f64(ptr a) {
+        double v;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+        return v;
+    }
+    static __device__ __forceinline__ uint32_t u32(ptr a) {
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+        return v;
+    }
+};
+template <>
+struct Mem<false> {
+    using ptr = const char*;
+    static __device__ __forceinline__ double f64(ptr a) { return __ldg(reinterpret_cast<const double*>(a)); }
+    static __device__ __forceinline__ uint32_t u32(ptr a) { return __ldg(reinterpret_cast<const uint32_t*>(a)); }
+};
+// one DistRec, read field by field on demand
 template <bool SMEM>
-__device__ __forceinline__ uint32_t guide_ld(const uint32_t* p) {
-    if constexpr (SMEM) return *p;
-    else return __ldg(p);
-}
+struct DistView {
+    typename Mem<SMEM>::ptr base;
+    __device__ __forceinline__ double p(int k) const { return Mem<SMEM>::f64(base + (32 + 8 * k)); }
+    __device__ __forceinline__ int flags() const { return int(Mem<SMEM>::u32(base + 16)); }
+    __device__ __forceinline__ int pad0() const { return int(Mem<SMEM>::u32(base + 20)); }
+    __device__ __forceinline__ int pad1() const { return int(Mem<SMEM>::u32(base + 24)); }
+};
+static_assert(offsetof(DistRec, flags) == 16 && offsetof(DistRec, pad0) == 20 && offsetof(DistRec, pad1) == 24 &&
+                  offsetof(DistRec, p) == 32,
+              "DistView offsets follow DistRec");
 
 // Inverse-CDF lookup with std::lower_bound semantics (first cp[i] >= u; libstdc++
 // random.tcc:2709-2713): the guide table (four buckets per entry) gives the first candidate, one
 // unconditional compare-and-step follows, and a scan loop that almost never iterates finishes.
 template <bool SMEM>
-__device__ __forceinline__ void emp_value2(const char* guide_b, const char* cp_b, uint32_t g, uint32_t len8, bool scan,
-                                           uint32_t hi_a, double ua, uint32_t hi_b, double ub, double& va, double& vb) {
+__device__ __forceinline__ void emp_value2(typename Mem<SMEM>::ptr guide_b, typename Mem<SMEM>::ptr cp_b, uint32_t g,
+                                           uint32_t len8, bool scan, uint32_t hi_a, double ua, uint32_t hi_b, double ub,
+                                           double& va, double& vb) {
     // floor(u * 2^g) == (X >> 12) >> (52 - g) == hi >> (32 - g),  1 <= g <= 20.  The two samples of
     // the lane are looked up in lockstep (one basic block) so their shared-memory latencies overlap.
     const uint32_t ja = hi_a >> (32u - g), jb = hi_b >> (32u - g);
-    uint32_t off_a = guide_ld<SMEM>(reinterpret_cast<const uint32_t*>(guide_b) + ja) * 8u;
-    uint32_t off_b = guide_ld<SMEM>(reinterpret_cast<const uint32_t*>(guide_b) + jb) * 8u;
-    const double ca = tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_a));
-    const double cb = tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_b));
+    uint32_t off_a = Mem<SMEM>::u32(guide_b + ja * 4u) * 8u;
+    uint32_t off_b = Mem<SMEM>::u32(guide_b + jb * 4u) * 8u;
+    const double ca = Mem<SMEM>::f64(cp_b + off_a);
+    const double cb = Mem<SMEM>::f64(cp_b + off_b);
     off_a += ca < ua ? 8u : 0u;  // cp[len-1] == 1.0 > u: stays in range
     off_b += cb < ub ? 8u : 0u;
     if (scan) {  // only tables whose guide buckets may hold several boundaries
-        while (tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_a)) < ua) off_a += 8u;
-        while (tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_b)) < ub) off_b += 8u;
+        while (Mem<SMEM>::f64(cp_b + off_a) < ua) off_a += 8u;
+        while (Mem<SMEM>::f64(cp_b + off_b) < ub) off_b += 8u;
     }
-    va = tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_a + len8));
-    vb = tab_ld<SMEM>(reinterpret_cast<const double*>(cp_b + off_b + len8));
+    va = Mem<SMEM>::f64(cp_b + off_a + len8);
+    vb = Mem<SMEM>::f64(cp_b + off_b + len8);
 }
 
 // (k + 1/2) * 2^-23 for the top 23 bits k of w: an fp32 uniform strictly inside (0,1), exact.
@@ -123,61 +151,67 @@ struct GammaHalf {  // the fp32-steered part of one attempt, split so that two a
     double v;
     bool pos, ok;
 };
-__device__ __forceinline__ void gamma_front(const DistRec& d, const Philox4& w, GammaHalf& h) {
+template <bool SMEM>
+__device__ __forceinline__ void gamma_front(const DistView<SMEM>& d, const Philox4& w, GammaHalf& h) {
     const float r2 = -1.3862943611198906f * lg2_approx(uniform23(w.x));  // -2 ln u1
     const float ang = float(int(w.y)) * 1.4629180792671596e-9f;           // 2 pi * int32 / 2^32, [-pi, pi)
     h.nf = sqrt_approx(fmaxf(r2, 0.0f)) * cos_approx(ang);
-    double v = fma(d.p[4], double(h.nf), 1.0);
+    double v = fma(d.p(4), double(h.nf), 1.0);
     h.pos = v > 0.0;
     h.v = v * v * v;
     h.u = uniform23(w.z);
     h.n2 = h.nf * h.nf;
     h.ok = h.u <= fmaf(-0.0331f * h.n2, h.n2, 1.0f);
 }
-__device__ __forceinline__ void gamma_exact(const DistRec& d, GammaHalf& h) {
+template <bool SMEM>
+__device__ __forceinline__ void gamma_exact(const DistView<SMEM>& d, GammaHalf& h) {
     // log(u) <= n^2/2 + d (1 - v + log v)
     const float vf = float(h.v);
     h.ok = 0.6931471805599453f * lg2_approx(h.u) <=
-           fmaf(0.5f, h.n2, float(d.p[3]) * (1.0f - vf + 0.6931471805599453f * lg2_approx(vf)));
+           fmaf(0.5f, h.n2, float(d.p(3)) * (1.0f - vf + 0.6931471805599453f * lg2_approx(vf)));
 }
-__device__ __forceinline__ bool gamma_back(const DistRec& d, const Philox4& w, const GammaHalf& h, double& x) {
-    x = d.p[6] * h.v;  // d * scale * v^3
-    if (d.flags & 1) x *= double(ex2_approx(lg2_approx(uniform23(w.w)) * float(d.p[5])));  // u^(1/shape), shape < 1
-    return h.pos && h.ok && x <= d.p[2];
+template <bool SMEM>
+__device__ __forceinline__ bool gamma_back(const DistView<SMEM>& d, const Philox4& w, const GammaHalf& h, double& x) {
+    x = d.p(6) * h.v;  // d * scale * v^3
+    if (d.flags() & 1) x *= double(ex2_approx(lg2_approx(uniform23(w.w)) * float(d.p(5))));  // u^(1/shape), shape < 1
+    return h.pos && h.ok && x <= d.p(2);
 }
-__device__ __forceinline__ bool gamma_eval(const DistRec& d, const Philox4& w, double& x) {
+template <bool SMEM>
+__device__ __forceinline__ bool gamma_eval(const DistView<SMEM>& d, const Philox4& w, double& x) {
     GammaHalf h;
-    gamma_front(d, w, h);
-    if (!h.ok) gamma_exact(d, h);
-    return gamma_back(d, w, h, x);
+    gamma_front<SMEM>(d, w, h);
+    if (!h.ok) gamma_exact<SMEM>(d, h);
+    return gamma_back<SMEM>(d, w, h, x);
 }
 // two attempts at once: one shared branch for the exact test, everything else straight-line
-__device__ __forceinline__ void gamma_eval2(const DistRec& d, const Philox4& wa, const Philox4& wb, double& xa,
+template <bool SMEM>
+__device__ __forceinline__ void gamma_eval2(const DistView<SMEM>& d, const Philox4& wa, const Philox4& wb, double& xa,
                                             double& xb, bool& ok_a, bool& ok_b) {
     GammaHalf ha, hb;
-    gamma_front(d, wa, ha);
-    gamma_front(d, wb, hb);
+    gamma_front<SMEM>(d, wa, ha);
+    gamma_front<SMEM>(d, wb, hb);
     if (!(ha.ok && hb.ok)) {
         const bool sa = ha.ok, sb = hb.ok;
-        gamma_exact(d, ha);
-        gamma_exact(d, hb);
+        gamma_exact<SMEM>(d, ha);
+        gamma_exact<SMEM>(d, hb);
         ha.ok = ha.ok || sa;  // a passed squeeze test stays accepted
         hb.ok = hb.ok || sb;
     }
-    ok_a = gamma_back(d, wa, ha, xa);
-    ok_b = gamma_back(d, wb, hb, xb);
+    ok_a = gamma_back<SMEM>(d, wa, ha, xa);
+    ok_b = gamma_back<SMEM>(d, wb, hb, xb);
 }
 
 // Gamma variates for the two samples of a thread.  First attempts run straight-line for both
 // samples; afterwards the whole warp iterates a uniform retry loop in which every lane retries one
 // pending sample, so a rejection costs the warp one extra attempt instead of one per sample.
-__device__ __forceinline__ void gamma_variate2(const DistRec& d, uint32_t seed_a, uint32_t seed_b, uint32_t act,
+template <bool SMEM>
+__device__ __forceinline__ void gamma_variate2(const DistView<SMEM>& d, uint32_t seed_a, uint32_t seed_b, uint32_t act,
                                                const PhiloxKeys& key0, double& xa, double& xb) {
     // both first-attempt blocks are generated back to back: two independent multiply chains in flight
     const Philox4 wa = philox4x32_10(seed_a, act, 0u, kTagSolo, key0);
     const Philox4 wb = philox4x32_10(seed_b, act, 0u, kTagSolo, key0);
     bool need_a, need_b;
-    gamma_eval2(d, wa, wb, xa, xb, need_a, need_b);
+    gamma_eval2<SMEM>(d, wa, wb, xa, xb, need_a, need_b);
     need_a = !need_a;
     need_b = !need_b;
     uint32_t ta = 1u, tb = 1u;
@@ -186,9 +220,9 @@ __device__ __forceinline__ void gamma_variate2(const DistRec& d, uint32_t seed_a
         const uint32_t seed = do_a ? seed_a : seed_b;
         const uint32_t t = do_a ? ta : tb;
         double x;
-        const bool ok = gamma_eval(d, philox4x32_10(seed, act, t, kTagSolo, key0), x);
+        const bool ok = gamma_eval<SMEM>(d, philox4x32_10(seed, act, t, kTagSolo, key0), x);
         const bool give_up = t + 1u >= kGammaMaxAttempts;  // the reference would spin forever: clamp
-        if (give_up) x = fmin(x, d.p[2]);
+        if (give_up) x = fmin(x, d.p(2));
         if (do_a) {
             ++ta;
             if (ok || give_up) {
@@ -220,7 +254,8 @@ __device__ __forceinline__ double half_term(uint32_t wu, uint32_t wa, uint32_t l
 }
 // words are consumed in order: k product uniforms, then (u', u'') of the half term.  `variant` = 2 * k + h
 // (warp-uniform): one straight-line case per supported shape.
-__device__ __forceinline__ double erlang_value(const DistRec& d, int variant, uint32_t w0, uint32_t w1, uint32_t w2,
+template <bool SMEM>
+__device__ __forceinline__ double erlang_value(const DistView<SMEM>& d, int variant, uint32_t w0, uint32_t w1, uint32_t w2,
                                                uint32_t w3, uint32_t log_tab) {
     double e;
     switch (variant) {
@@ -232,39 +267,41 @@ __device__ __forceinline__ double erlang_value(const DistRec& d, int variant, ui
         case 6: e = -log_pos(uniform32(w0) * uniform32(w1) * uniform32(w2), log_tab); break;             // 3
         default: e = -log_pos((uniform32(w0) * uniform32(w1)) * (uniform32(w2) * uniform32(w3)), log_tab); break;  // 4
     }
-    return d.p[1] * e;
+    return d.p(1) * e;
 }
 
 // draw j of both samples; one Philox block serves the seed pair when a sample needs <= 2 words
-__device__ __forceinline__ void erlang_draw2(const DistRec& d, int variant, uint32_t seed_a, uint32_t seed_b, bool paired,
+template <bool SMEM>
+__device__ __forceinline__ void erlang_draw2(const DistView<SMEM>& d, int variant, uint32_t seed_a, uint32_t seed_b, bool paired,
                                              uint32_t act, uint32_t ja, uint32_t jb, const PhiloxKeys& key0,
                                              uint32_t log_tab, double& ya, double& yb) {
     if (variant <= 2 || variant == 4) {  // <= 64 bits per sample
         if (paired && ja == jb) {
             const Philox4 r = philox4x32_10(seed_a >> 1, act, ja, kTagErlang, key0);
-            ya = erlang_value(d, variant, r.x, r.y, 0u, 0u, log_tab);
-            yb = erlang_value(d, variant, r.z, r.w, 0u, 0u, log_tab);
+            ya = erlang_value<SMEM>(d, variant, r.x, r.y, 0u, 0u, log_tab);
+            yb = erlang_value<SMEM>(d, variant, r.z, r.w, 0u, 0u, log_tab);
         } else {
             const Philox4 ra = philox4x32_10(seed_a >> 1, act, ja, kTagErlang, key0);
             const Philox4 rb = philox4x32_10(seed_b >> 1, act, jb, kTagErlang, key0);
             const bool oa = seed_a & 1u, ob = seed_b & 1u;
-            ya = erlang_value(d, variant, oa ? ra.z : ra.x, oa ? ra.w : ra.y, 0u, 0u, log_tab);
-            yb = erlang_value(d, variant, ob ? rb.z : rb.x, ob ? rb.w : rb.y, 0u, 0u, log_tab);
+            ya = erlang_value<SMEM>(d, variant, oa ? ra.z : ra.x, oa ? ra.w : ra.y, 0u, 0u, log_tab);
+            yb = erlang_value<SMEM>(d, variant, ob ? rb.z : rb.x, ob ? rb.w : rb.y, 0u, 0u, log_tab);
         }
     } else {
         const Philox4 ra = philox4x32_10(seed_a, act, ja, kTagErlang, key0);
         const Philox4 rb = philox4x32_10(seed_b, act, jb, kTagErlang, key0);
-        ya = erlang_value(d, variant, ra.x, ra.y, ra.z, ra.w, log_tab);
-        yb = erlang_value(d, variant, rb.x, rb.y, rb.z, rb.w, log_tab);
+        ya = erlang_value<SMEM>(d, variant, ra.x, ra.y, ra.z, ra.w, log_tab);
+        yb = erlang_value<SMEM>(d, variant, rb.x, rb.y, rb.z, rb.w, log_tab);
     }
 }
 
-__device__ __forceinline__ void erlang_variate2(const DistRec& d, uint32_t seed_a, uint32_t seed_b, bool paired,
+template <bool SMEM>
+__device__ __forceinline__ void erlang_variate2(const DistView<SMEM>& d, uint32_t seed_a, uint32_t seed_b, bool paired,
                                                 uint32_t act, const PhiloxKeys& key0, uint32_t log_tab, double& xa,
                                                 double& xb) {
-    const int variant = 2 * d.pad0 + d.pad1;
-    const double mx = d.p[2];
-    erlang_draw2(d, variant, seed_a, seed_b, paired, act, 0u, 0u, key0, log_tab, xa, xb);
+    const int variant = 2 * d.pad0() + d.pad1();
+    const double mx = d.p(2);
+    erlang_draw2<SMEM>(d, variant, seed_a, seed_b, paired, act, 0u, 0u, key0, log_tab, xa, xb);
     // truncation (_core.cpp:98-104): draws 1, 2, ... until x <= max_scale; rare, so off the straight path
     bool need_a = xa > mx, need_b = xb > mx;
     if (__any_sync(0xFFFFFFFFu, need_a || need_b)) {
@@ -273,7 +310,7 @@ __device__ __forceinline__ void erlang_variate2(const DistRec& d, uint32_t seed_
             ja += need_a ? 1u : 0u;
             jb += need_b ? 1u : 0u;
             double ya, yb;
-            erlang_draw2(d, variant, seed_a, seed_b, paired, act, ja, jb, key0, log_tab, ya, yb);
+            erlang_draw2<SMEM>(d, variant, seed_a, seed_b, paired, act, ja, jb, key0, log_tab, ya, yb);
             if (need_a) {
                 xa = ya;
                 need_a = ya > mx && ja + 1u < kGammaMaxAttempts;
@@ -293,21 +330,23 @@ __device__ __forceinline__ void erlang_variate2(const DistRec& d, uint32_t seed_
 // {2k, 2k+1}, so one PAIR block serves both.  Returns extra (the value Dist::sample returns); the
 // caller forms base + extra with separately rounded operations like the reference build.
 template <bool SMEM>
-__device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, const DistRec* dists, uint32_t dist,
-                                              const double* tab, double base, uint32_t act, uint32_t seed_a,
-                                              uint32_t seed_b, bool paired, const PhiloxKeys& key0, uint32_t log_tab,
-                                              double& ea, double& eb) {
+__device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, typename Mem<SMEM>::ptr dists,
+                                              uint32_t dist, typename Mem<SMEM>::ptr tab, double base, uint32_t act,
+                                              uint32_t seed_a, uint32_t seed_b, bool paired, const PhiloxKeys& key0,
+                                              uint32_t log_tab, double& ea, double& eb) {
     const uint32_t kind = meta >> 29;
     if (kind == MCDP_DIST_CONSTANT) {
-        ea = eb = __dmul_rn(base, dists[dist].p[0]);  // _core.cpp:75
+        const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
+        ea = eb = __dmul_rn(base, d.p(0));  // _core.cpp:75
         return;
     }
     if (kind == MCDP_DIST_GAMMA) {
+        const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
         double xa, xb;
-        if (dists[dist].flags & 8)
-            erlang_variate2(dists[dist], seed_a, seed_b, paired, act, key0, log_tab, xa, xb);
+        if (d.flags() & 8)
+            erlang_variate2<SMEM>(d, seed_a, seed_b, paired, act, key0, log_tab, xa, xb);
         else
-            gamma_variate2(dists[dist], seed_a, seed_b, act, key0, xa, xb);
+            gamma_variate2<SMEM>(d, seed_a, seed_b, act, key0, xa, xb);
         ea = __dmul_rn(xa, base);
         eb = __dmul_rn(xb, base);
         return;
@@ -333,10 +372,10 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, c
     if (kind == MCDP_DIST_EXPONENTIAL) {
         // inverse CDF of the exponential truncated to [0, max_scale]: the law of the
         // reference's rejection loop (_core.cpp:83-89), without the loop.
-        const DistRec& d = dists[dist];
-        const double lam = d.p[0], mx = d.p[1], F = d.p[2];
+        const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
+        const double lam = d.p(0), mx = d.p(1), F = d.p(2);
         double xa, xb;
-        if (d.flags & 2) {  // F < 2^-10: series keeps the relative accuracy (both samples in one block)
+        if (d.flags() & 2) {  // F < 2^-10: series keeps the relative accuracy (both samples in one block)
             xa = lam * neg_log1m(ua * F, true, log_tab);
             xb = lam * neg_log1m(ub * F, true, log_tab);
         } else {
@@ -353,8 +392,8 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, c
     // carries the byte offsets of guide (tab_off) and cp (dist)
     const uint32_t g = (meta >> 24) & 31u, len8 = (meta & 0x7FFFFFu) * 8u;
     const bool scan = meta & 0x800000u;
-    const char* guide_b = reinterpret_cast<const char*>(tab) + tab_off;
-    const char* cp_b = reinterpret_cast<const char*>(tab) + dist;
+    const typename Mem<SMEM>::ptr guide_b = tab + tab_off;
+    const typename Mem<SMEM>::ptr cp_b = tab + dist;
     double va, vb;
     emp_value2<SMEM>(guide_b, cp_b, g, len8, scan, hi_a, ua, hi_b, ub, va, vb);
     if (kind == MCDP_DIST_EMP_ABS) {  // _core.cpp:125

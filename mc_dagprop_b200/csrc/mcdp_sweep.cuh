@@ -49,6 +49,8 @@ struct SweepParams {
     double hist_lo, hist_scale;
     double max_delay;
     int64_t n, ld;
+    uint32_t ldb8, ldb4;                // ld * 8, ld * 4 (row strides in bytes, < 2^32)
+    uint32_t smem_tab_off, smem_ring_off;  // dynamic shared memory: byte offsets of the table pool and of the chunk rings
     int32_t n_levels, n_orphans, n_dists, tab_pool_len;
     int32_t n_thresholds, n_bins, E, n_chunks;
     uint32_t last_pred;  // index of the last precedence record (prefetch clamp)
@@ -77,24 +79,27 @@ __device__ __forceinline__ double ref_min(double a, double b) { return (b < a) ?
 template <int MODE, bool SMEM, bool MULTI = false>
 __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS) sweep_kernel(const __grid_constant__ SweepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const DistRec* dists = p.dists;
-    const double* tab = p.tab_pool;
     // the log table of mcdp_math.cuh opens the dynamic shared memory
+    uint32_t smem_base = uint32_t(__cvta_generic_to_shared(smem_raw));
+    asm volatile("" : "+r"(smem_base));
     for (int i = threadIdx.x; i < kLogTabEntries; i += blockDim.x)
         reinterpret_cast<int4*>(smem_raw)[i] = __ldg(reinterpret_cast<const int4*>(p.log_tab) + i);
-    const uint32_t log_tab = uint32_t(__cvta_generic_to_shared(smem_raw));
+    const uint32_t log_tab = smem_base;
     size_t smem_used = kLogTabBytes;
+    typename Mem<SMEM>::ptr dists, tab;
     if constexpr (SMEM) {
         // stage distribution records + guide / inverse-CDF tables once per CTA
-        DistRec* s_dists = reinterpret_cast<DistRec*>(smem_raw + kLogTabBytes);
-        double* s_tab = reinterpret_cast<double*>(smem_raw + kLogTabBytes + sizeof(DistRec) * p.n_dists);
+        int4* s_dists = reinterpret_cast<int4*>(smem_raw + kLogTabBytes);
+        double* s_tab = reinterpret_cast<double*>(smem_raw + p.smem_tab_off);
         const int n16 = int(sizeof(DistRec) / 16) * p.n_dists;
-        for (int i = threadIdx.x; i < n16; i += blockDim.x)
-            reinterpret_cast<int4*>(s_dists)[i] = __ldg(reinterpret_cast<const int4*>(p.dists) + i);
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) s_dists[i] = __ldg(reinterpret_cast<const int4*>(p.dists) + i);
         for (int i = threadIdx.x; i < p.tab_pool_len; i += blockDim.x) s_tab[i] = __ldg(p.tab_pool + i);
-        dists = s_dists;
-        tab = s_tab;
+        dists = smem_base + uint32_t(kLogTabBytes);
+        tab = smem_base + p.smem_tab_off;
         smem_used = kLogTabBytes + sizeof(DistRec) * p.n_dists + sizeof(double) * p.tab_pool_len;
+    } else {
+        dists = reinterpret_cast<const char*>(p.dists);
+        tab = reinterpret_cast<const char*>(p.tab_pool);
     }
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;

@@ -3,6 +3,8 @@ import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from mc_dagprop_b200 import capi, synth
+if os.environ.get("MCDP_LIB"):  # scratch A/B builds
+    capi.LIB_PATH = os.path.abspath(os.environ["MCDP_LIB"])
 
 def run(name, dag, dists, n, wpg=0, gpc=0, reps=3):
     plan = capi.Plan(dag, dists, device=0)
