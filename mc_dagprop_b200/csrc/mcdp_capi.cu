@@ -99,9 +99,16 @@ struct mcdp_plan {
     // event + precedence records live in ONE allocation so that a single L2 access-policy window
     // (persisting) covers the whole stream: 128 GB of streaming output per launch would otherwise
     // keep evicting the records every warp re-reads
-    DevBuf<ChunkUnit> d_chunks;           // full / injected modes
-    DevBuf<int32_t> d_chunk_level_begin;
-    DevBuf<unsigned char> d_stream_red;   // reduced mode: event + precedence records
+    // chunk streams [rows: 0 event ids (full / injected), 1 scratch slots (reduced)][0 level-aligned, 1 dense]
+    struct ChunkStreamDev {
+        DevBuf<ChunkUnit> units;
+        DevBuf<int32_t> level_begin;
+        int32_t n_chunks = 0;
+        bool ready = false;
+    } streams[2][2];
+    DevBuf<unsigned char> d_stream_red;   // reduced mode, several batches per group: event + precedence records
+    std::vector<EventRec> ev_red;         // host copies of the slot-row records (built once)
+    std::vector<PredRec> pr_red;
     size_t l2_persist_bytes = 0, l2_window_max = 0;
     struct RecPtrs {
         EventRec* p = nullptr;
@@ -129,13 +136,17 @@ struct mcdp_plan {
     DevBuf<double> d_stat_f64;
     DevBuf<unsigned long long> d_stat_u64;
     DevBuf<uint32_t> d_stat_u32;
+    std::mutex stream_mu;  // lazy construction of the chunk streams
     std::mutex mu;  // instances are not re-entrant in the reference either; serialise instead of corrupting scratch
 
     ~mcdp_plan() {
         DeviceGuard g(device);
         for (auto& s : slots) s.release();
-        d_chunks.release();
-        d_chunk_level_begin.release();
+        for (auto& a : streams)
+            for (auto& st : a) {
+                st.units.release();
+                st.level_begin.release();
+            }
         d_stream_red.release();
         d_level_begin.release();
         d_orphans.release();
@@ -262,20 +273,25 @@ int32_t launch_kernel(mcdp_plan* plan, K k, const SweepParams& p, const LaunchSh
     return MCDP_OK;
 }
 
+int32_t ensure_chunk_stream(mcdp_plan* plan, bool reduced, bool dense, SweepParams& p);
+
 template <int MODE>
-int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p, const LaunchShape& s, cudaStream_t stream) {
-    if (p.n <= 0) return MCDP_OK;
+int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p_in, const LaunchShape& s, cudaStream_t stream) {
+    if (p_in.n <= 0) return MCDP_OK;
+    SweepParams p = p_in;
     if constexpr (MODE == kModeReduced) {
         // event + precedence record streams (mcdp_sweep.cuh)
         const size_t bytes = size_t(plan->host.E) * sizeof(EventRec) + size_t(plan->host.P) * sizeof(PredRec);
         if (s.batches > 1)
             return s.smem_tables ? launch_kernel(plan, sweep_kernel<MODE, true, true>, p, s, s.smem, p.events, bytes, stream)
                                  : launch_kernel(plan, sweep_kernel<MODE, false, true>, p, s, s.smem, p.events, bytes, stream);
-        return s.smem_tables ? launch_kernel(plan, sweep_kernel<MODE, true, false>, p, s, s.smem, p.events, bytes, stream)
-                             : launch_kernel(plan, sweep_kernel<MODE, false, false>, p, s, s.smem, p.events, bytes, stream);
-    } else {
-        // chunk stream (mcdp_chunk_sweep.cuh): tables (128-byte rounded) + per-warp chunk ring
-        const size_t bytes = size_t(plan->host.n_chunks) * size_t(kChunkBytes);
+    }
+    {
+        // chunk stream (mcdp_chunk_sweep.cuh): tables (128-byte rounded) + per-warp chunk ring.  One warp per
+        // group walks the dense stream, several warps per group split the level-aligned one.
+        const int32_t rc = ensure_chunk_stream(plan, MODE == kModeReduced, s.wpg == 1, p);
+        if (rc) return rc;
+        const size_t bytes = size_t(p.n_chunks) * size_t(kChunkBytes);
         const size_t smem = ((s.smem + 127) & ~size_t(127)) + chunk_ring_bytes(s.threads / 32);
         if (s.wpg > 1)
             return s.smem_tables ? launch_kernel(plan, chunk_sweep_kernel<MODE, true, true>, p, s, smem, p.chunks, bytes, stream)
@@ -288,9 +304,6 @@ int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p, const LaunchShape& s
 SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, int64_t ld) {
     SweepParams p{};
     const HostPlan& h = plan->host;
-    p.chunks = plan->d_chunks.p;
-    p.chunk_level_begin = plan->d_chunk_level_begin.p;
-    p.n_chunks = h.n_chunks;
     p.level_begin = plan->d_level_begin.p;
     p.orphans = plan->d_orphans.p;
     p.dists = plan->d_dists.p;
@@ -337,8 +350,10 @@ int32_t launch_transpose(const T* in, int64_t in_ld, int64_t rows, int64_t cols,
 int32_t ensure_reduced_stream(mcdp_plan* plan) {
     if (plan->red_ready) return MCDP_OK;
     const HostPlan& h = plan->host;
-    std::vector<EventRec> ev = h.events;
-    std::vector<PredRec> pr = h.preds;
+    std::vector<EventRec>& ev = plan->ev_red;
+    std::vector<PredRec>& pr = plan->pr_red;
+    ev = h.events;
+    pr = h.preds;
     for (auto& q : pr) q.src_row = h.slot_of_event[q.src_row];  // host stream rows are event ids
     for (auto& e : ev) {
         e.row = h.slot_of_event[e.event];
@@ -349,6 +364,39 @@ int32_t ensure_reduced_stream(mcdp_plan* plan) {
     int32_t rc = upload_stream(plan->d_stream_red, ev, pr, &plan->d_events_red.p, &plan->d_preds_red.p);
     if (rc) return rc;
     plan->red_ready = true;
+    return MCDP_OK;
+}
+
+// the chunk stream a launch needs: built and uploaded on first use
+int32_t ensure_chunk_stream(mcdp_plan* plan, bool reduced, bool dense, SweepParams& p) {
+    std::lock_guard<std::mutex> lock(plan->stream_mu);
+    mcdp_plan::ChunkStreamDev& st = plan->streams[reduced ? 1 : 0][dense ? 1 : 0];
+    if (!st.ready) {
+        const HostPlan& h = plan->host;
+        if (reduced) {
+            int32_t rc = ensure_reduced_stream(plan);
+            if (rc) return rc;
+        }
+        std::vector<ChunkUnit> units;
+        std::vector<int32_t> clb;
+        const std::vector<ChunkUnit>* src = &units;
+        const std::vector<int32_t>* src_clb = &clb;
+        if (!reduced && !dense) {
+            src = &h.units;
+            src_clb = &h.chunk_level_begin;
+        } else {
+            build_chunk_stream(reduced ? plan->ev_red : h.events, reduced ? plan->pr_red : h.preds, h.level_begin, h.n_levels,
+                               dense, units, clb);
+        }
+        int32_t rc = upload(st.units, *src);
+        if (!rc) rc = upload(st.level_begin, *src_clb);
+        if (rc) return rc;
+        st.n_chunks = int32_t(src->size() / size_t(kChunkUnits));
+        st.ready = true;
+    }
+    p.chunks = st.units.p;
+    p.chunk_level_begin = st.level_begin.p;
+    p.n_chunks = st.n_chunks;
     return MCDP_OK;
 }
 
@@ -456,9 +504,7 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
             cudaGetLastError();
     }
     const HostPlan& h = plan->host;
-    int32_t rc = upload(plan->d_chunks, h.units);
-    if (!rc) rc = upload(plan->d_chunk_level_begin, h.chunk_level_begin);
-    if (!rc) rc = upload(plan->d_level_begin, h.level_begin);
+    int32_t rc = upload(plan->d_level_begin, h.level_begin);
     if (!rc) rc = upload(plan->d_orphans, h.orphans);
     if (!rc) rc = upload(plan->d_dists, h.dists);
     if (!rc) rc = upload(plan->d_tab, h.tab_pool);

@@ -1,5 +1,5 @@
-// mcdp_chunk_sweep.cuh -- fused sample + max-plus sweep over the chunk stream (full and
-// duration-injection modes), sm_100a.
+// mcdp_chunk_sweep.cuh -- fused sample + max-plus sweep over the chunk stream (full, duration-injection
+// and single-batch reduced-statistics modes), sm_100a.
 //
 // Replaces Simulator::run (reference _core.cpp:312-353) for a block of seeds.  Same data layout
 // and work split as mcdp_sweep.cuh (a warp owns 64 adjacent samples, two per lane;
@@ -65,7 +65,6 @@ __host__ __device__ inline size_t chunk_ring_bytes(int n_warps) { return size_t(
 template <int MODE, bool SMEM, bool DYN>
 __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
     chunk_sweep_kernel(const __grid_constant__ SweepParams p) {
-    static_assert(MODE == kModeFull || MODE == kModeInjected, "reduced mode runs sweep_kernel");
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     // Dynamic shared memory: [log table][DistRec[] + table pool (SMEM)][per-warp chunk rings].  Everything
     // is addressed through ONE shared-window base register (kept opaque so that it is not re-derived
@@ -132,7 +131,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
     auto i32_row = [&](const void* base, uint32_t row) -> char* {
         return const_cast<char*>(reinterpret_cast<const char*>(base)) + (uint64_t(row) * p.ldb4 + (lane_off >> 1));
     };
-    const void* const dur_base = MODE == kModeFull ? static_cast<const void*>(p.durations) : static_cast<const void*>(p.inj);
+    const void* const dur_base = MODE == kModeInjected ? static_cast<const void*>(p.inj) : static_cast<const void*>(p.durations);
 
     // ---- chunk pipeline: the ring's buffers alternate; `phase` holds the mbarrier parity of each ----
     uint32_t buf_sel = 0u, phase = 0u;
@@ -167,11 +166,56 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
     double lat_a = 0.0, lat_b = 0.0, ub = 0.0;
     int cause_a = -1, cause_b = -1;
     double2 nrs = make_double2(0.0, 0.0);
+    uint32_t ev = 0u;        // reduced mode: event id (row is a recycled scratch slot there)
+    double ev_earliest = 0.0;
+    const bool valid_a = s0 < p.n, valid_b = s0 + 1 < p.n;
     auto finalize = [&]() {
         // _core.cpp:348-349.  realized rows are gathered by other warps: L2 only (st.cg / ld.cg)
-        __stcg(reinterpret_cast<double2*>(f64_row(p.realized, row)), make_double2(ref_min(lat_a, ub), ref_min(lat_b, ub)));
-        __stcs(reinterpret_cast<int2*>(i32_row(p.cause, row)), make_int2(cause_a, cause_b));
+        const double ra = ref_min(lat_a, ub), rb = ref_min(lat_b, ub);
+        __stcg(reinterpret_cast<double2*>(f64_row(p.realized, row)), make_double2(ra, rb));
         open = false;
+        if constexpr (!DYN) {  // a following header may take the closed event's value over (forward)
+            lat_a = ra;
+            lat_b = rb;
+        }
+        if constexpr (MODE != kModeReduced) {
+            __stcs(reinterpret_cast<int2*>(i32_row(p.cause, row)), make_int2(cause_a, cause_b));
+        } else {
+            // per-event statistics of the delay realized - earliest over this warp's 64 samples: one
+            // atomic per statistic (and per distinct histogram bin) per warp
+            const double xa = valid_a ? ra - ev_earliest : 0.0;
+            const double xb = valid_b ? rb - ev_earliest : 0.0;
+            if (p.sum) {
+                const double t = warp_sum(xa + xb);
+                if (lane == 0) atomicAdd(p.sum + ev, t);
+            }
+            if (p.sumsq) {
+                const double t = warp_sum(xa * xa + xb * xb);
+                if (lane == 0) atomicAdd(p.sumsq + ev, t);
+            }
+            if (p.late) {
+#pragma unroll
+                for (int t = 0; t < MCDP_MAX_THRESHOLDS; ++t) {
+                    if (t < p.n_thresholds) {
+                        const int cnt = __reduce_add_sync(
+                            0xFFFFFFFFu, int(valid_a && xa > p.thresholds[t]) + int(valid_b && xb > p.thresholds[t]));
+                        if (lane == 0 && cnt) atomicAdd(p.late + size_t(t) * p.E + ev, (unsigned long long)cnt);
+                    }
+                }
+            }
+            if (p.hist) {
+                const int nb = p.n_bins;
+                int ba = min(max(int(floor((xa - p.hist_lo) * p.hist_scale)), 0), nb - 1);
+                int bb = min(max(int(floor((xb - p.hist_lo) * p.hist_scale)), 0), nb - 1);
+                if (!valid_a) ba = -1 - lane;  // unique keys: match groups of size 1, skipped below
+                if (!valid_b) bb = -1 - lane;
+                uint32_t* h = p.hist + size_t(ev) * nb;
+                const unsigned ga = __match_any_sync(0xFFFFFFFFu, ba);
+                if (ba >= 0 && lane == __ffs(ga) - 1) atomicAdd(h + ba, uint32_t(__popc(ga)));
+                const unsigned gb = __match_any_sync(0xFFFFFFFFu, bb);
+                if (bb >= 0 && lane == __ffs(gb) - 1) atomicAdd(h + bb, uint32_t(__popc(gb)));
+            }
+        }
     };
     auto process = [&](uint32_t buf, int u0, uint32_t remaining) {
 #pragma unroll 1
@@ -180,16 +224,31 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
             const int4 q1 = lds128(buf + uint32_t(u) * 32u + 16u);
             const uint32_t meta = uint32_t(q1.x);
             const uint32_t kind = meta >> 29;
-            // the realized row of the NEXT entry unit is requested before this unit's delay is drawn
-            // (q1.z: PredRec::next_src_row / HeaderUnit::first_src_row)
+            // The realized row of the NEXT entry unit is requested before this unit's delay is drawn (q1.z:
+            // PredRec::next_src_row / HeaderUnit::first_src_row).  In a dense stream (!DYN) a header may ask for
+            // the row of the event that is closed at this very header: there the request follows the close.
             const double2 rs = nrs;
-            if (uint32_t(q1.z) != kNoRow) nrs = __ldcg(reinterpret_cast<const double2*>(f64_row(p.realized, uint32_t(q1.z))));
+            if (DYN || kind < kKindEvent) {
+                if (uint32_t(q1.z) != kNoRow)
+                    nrs = __ldcg(reinterpret_cast<const double2*>(f64_row(p.realized, uint32_t(q1.z))));
+            }
             if (kind >= kKindEvent) {
                 if (open) finalize();
                 if (kind == kKindEnd) break;
+                if constexpr (!DYN) {
+                    // the first entry's source: taken over from the event this warp has just closed
+                    // (HeaderUnit::pad), or requested now
+                    if (q1.w != 0) nrs = make_double2(lat_a, lat_b);
+                    else if (uint32_t(q1.z) != kNoRow)
+                        nrs = __ldcg(reinterpret_cast<const double2*>(f64_row(p.realized, uint32_t(q1.z))));
+                }
                 // _core.cpp:333-337
                 row = uint32_t(q0.x);
                 const double earliest = __hiloint2double(q0.w, q0.z);
+                if constexpr (MODE == kModeReduced) {
+                    ev = uint32_t(q0.y);
+                    ev_earliest = earliest;
+                }
                 ub = __dadd_rn(earliest, p.max_delay);
                 lat_a = lat_b = earliest;
                 cause_a = cause_b = -1;
@@ -214,7 +273,9 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
                     da = __dadd_rn(base, ea);  // _core.cpp:328
                     db = __dadd_rn(base, eb);
                 }
-                if (act != kNoAct) __stcs(reinterpret_cast<double2*>(f64_row(dur_base, act)), make_double2(da, db));
+                if constexpr (MODE == kModeFull) {
+                    if (act != kNoAct) __stcs(reinterpret_cast<double2*>(f64_row(dur_base, act)), make_double2(da, db));
+                }
             }
             // _core.cpp:341-346
             const double ta = ref_min(__dadd_rn(rs.x, da), ub);

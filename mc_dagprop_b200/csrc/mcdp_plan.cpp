@@ -194,31 +194,64 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
 // Gather-prefetch links of a chunk stream: every entry unit names the source row of the next
 // entry unit its warp will process (the next event of the chunk and continuation chunks
 // included); the chunk-opening header names the first entry's.
-void link_chunk_gathers(std::vector<ChunkUnit>& units) {
+// A dense stream (one warp walks all chunks in order, chunks span levels) may put an event right
+// behind one of its own predecessors.  Its first entry then must not be requested while that
+// predecessor is still open: the link is cut and the header takes the value over from the
+// registers of the event the warp has just closed (`forward`).
+void link_chunk_gathers(std::vector<ChunkUnit>& units, bool dense) {
     constexpr size_t U = size_t(kChunkUnits);
     auto kind_of = [](const ChunkUnit& u) { return u.pred.meta >> 29; };
     const size_t n_chunks = units.size() / U;
+    uint32_t prev_chunk_last_row = kNoRow;  // row of the event the previous chunk closed last
     for (size_t c = 0; c < n_chunks; ++c) {
         ChunkUnit* ch = &units[c * U];
         const bool cont_in = kind_of(ch[0]) == kKindEnd;  // continuation header: the previous chunk links into this one
-        int last_pred = -1;
+        int last_pred = -1, last_pred_head = -1;
+        int head = -1;  // header unit of the event being walked
+        uint32_t last_row = kNoRow;
         for (size_t u = 0; u < U; ++u) {
             const uint32_t k = kind_of(ch[u]);
             if (u > 0 && k == kKindEnd) break;
-            if (k >= kKindEvent) continue;
-            if (last_pred < 0) {
-                if (cont_in) {
-                    // last entry unit of the previous chunk (always unit U-1 of a full chunk)
-                    units[c * U - 1].pred.next_src_row = ch[u].pred.src_row;
-                } else {
-                    ch[0].head.first_src_row = ch[u].pred.src_row;
-                }
-            } else {
-                ch[last_pred].pred.next_src_row = ch[u].pred.src_row;
+            if (k >= kKindEvent) {
+                head = int(u);
+                last_row = ch[u].head.row;
+                continue;
             }
+            const uint32_t src = ch[u].pred.src_row;
             ch[u].pred.next_src_row = kNoRow;
+            // the unit that requests this entry's source row one step early
+            const int link_head = last_pred >= 0 ? last_pred_head : 0;
+            bool linked = false;
+            if (dense && head != link_head && !(last_pred < 0 && cont_in)) {
+                // rows of the events that are still open or not yet started when the early request would be issued
+                bool hazard = false;
+                uint32_t before = kNoRow;  // row of the event closed right before `head`
+                for (int v = link_head; v < head; ++v)
+                    if (kind_of(ch[v]) >= kKindEvent) {
+                        hazard = hazard || ch[v].head.row == src;
+                        before = ch[v].head.row;
+                    }
+                if (hazard) {
+                    if (src == before) ch[head].head.pad = 1u;  // forward from the registers of the event just closed
+                    else ch[head].head.first_src_row = src;     // request at the header, after the close
+                    linked = true;
+                }
+            }
+            if (!linked) {
+                if (last_pred >= 0) {
+                    ch[last_pred].pred.next_src_row = src;
+                } else if (cont_in) {
+                    units[c * U - 1].pred.next_src_row = src;  // last entry unit of the previous (full) chunk
+                } else if (dense && head == 0 && src == prev_chunk_last_row) {
+                    ch[0].head.pad = 1u;  // the previous chunk's last event is still in this warp's registers
+                } else {
+                    ch[0].head.first_src_row = src;
+                }
+            }
             last_pred = int(u);
+            last_pred_head = head;
         }
+        if (last_row != kNoRow) prev_chunk_last_row = last_row;
     }
 }
 
@@ -226,9 +259,16 @@ void link_chunk_gathers(std::vector<ChunkUnit>& units) {
 // the chunks shrink towards the end (guided self-scheduling: a chunk takes about 1/32 of the units
 // still to go, at least 6), so that the warps which split a level reach its barrier within an
 // event or two of each other while most of the level is still handed out as full 512-byte chunks.
-void build_chunk_stream(HostPlan& out) {
-    out.units.clear();
-    out.chunk_level_begin.assign(size_t(out.n_levels) + 1, 0);
+void build_chunk_stream_impl(const std::vector<EventRec>& events, const std::vector<PredRec>& preds,
+                             const std::vector<int32_t>& level_begin_in, int32_t n_levels_in, bool dense,
+                             std::vector<ChunkUnit>& units, std::vector<int32_t>& chunk_level_begin) {
+    units.clear();
+    // dense: one span over all events (no level alignment, full chunks); for launches in which one warp walks
+    // the whole stream
+    const std::vector<int32_t> one_span = {0, int32_t(events.size())};
+    const std::vector<int32_t>& level_begin = dense ? one_span : level_begin_in;
+    const int32_t n_levels = dense ? (events.empty() ? 0 : 1) : n_levels_in;
+    chunk_level_begin.assign(size_t(n_levels) + 1, 0);
     constexpr uint32_t U = uint32_t(kChunkUnits);
     auto end_unit = [] {
         ChunkUnit u{};
@@ -247,27 +287,27 @@ void build_chunk_stream(HostPlan& out) {
         return u;
     };
     auto pad_chunk = [&] {
-        while (out.units.size() % U) out.units.push_back(end_unit());
+        while (units.size() % U) units.push_back(end_unit());
     };
-    for (int32_t l = 0; l < out.n_levels; ++l) {
-        const int32_t pb = out.level_begin[l], pe = out.level_begin[size_t(l) + 1];
+    for (int32_t l = 0; l < n_levels; ++l) {
+        const int32_t pb = level_begin[l], pe = level_begin[size_t(l) + 1];
         int64_t units_left = 0;
-        for (int32_t p = pb; p < pe; ++p) units_left += 1 + int64_t(out.events[p].fan_in);
+        for (int32_t p = pb; p < pe; ++p) units_left += 1 + int64_t(events[p].fan_in);
         uint32_t pos = 0;        // units used in the open chunk
         uint32_t budget = U;     // units the open chunk may take
         for (int32_t p = pb; p < pe; ++p) {
-            const EventRec& ev = out.events[p];
+            const EventRec& ev = events[p];
             const uint32_t need = 1u + ev.fan_in;
             if (need > U) {  // long event: own run of chunks, 15 entries each
                 pad_chunk();
                 const uint32_t per = U - 1u;
                 const uint32_t n_ch = (ev.fan_in + per - 1u) / per;
                 for (uint32_t j = 0; j < n_ch; ++j) {
-                    out.units.push_back(header(ev, j > 0, n_ch - 1u - j));
+                    units.push_back(header(ev, j > 0, n_ch - 1u - j));
                     for (uint32_t k = j * per; k < std::min(ev.fan_in, (j + 1u) * per); ++k) {
                         ChunkUnit u{};
-                        u.pred = out.preds[ev.pred_begin + k];
-                        out.units.push_back(u);
+                        u.pred = preds[ev.pred_begin + k];
+                        units.push_back(u);
                     }
                 }
                 pad_chunk();
@@ -277,12 +317,12 @@ void build_chunk_stream(HostPlan& out) {
                     pad_chunk();
                     pos = 0;
                 }
-                if (pos == 0) budget = uint32_t(std::min<int64_t>(U, std::max<int64_t>(6, units_left / 32)));
-                out.units.push_back(header(ev, false, 0));
+                if (pos == 0) budget = dense ? U : uint32_t(std::min<int64_t>(U, std::max<int64_t>(6, units_left / 32)));
+                units.push_back(header(ev, false, 0));
                 for (uint32_t k = 0; k < ev.fan_in; ++k) {
                     ChunkUnit u{};
-                    u.pred = out.preds[ev.pred_begin + k];
-                    out.units.push_back(u);
+                    u.pred = preds[ev.pred_begin + k];
+                    units.push_back(u);
                 }
                 pos += need;
                 if (pos >= U) pos = 0;  // exactly full
@@ -290,13 +330,18 @@ void build_chunk_stream(HostPlan& out) {
             units_left -= need;
         }
         pad_chunk();
-        out.chunk_level_begin[size_t(l) + 1] = int32_t(out.units.size() / U);
+        chunk_level_begin[size_t(l) + 1] = int32_t(units.size() / U);
     }
-    out.n_chunks = int32_t(out.units.size() / U);
-    link_chunk_gathers(out.units);
+    link_chunk_gathers(units, dense);
 }
 
 }  // namespace
+
+void build_chunk_stream(const std::vector<EventRec>& events, const std::vector<PredRec>& preds,
+                        const std::vector<int32_t>& level_begin, int32_t n_levels, bool dense, std::vector<ChunkUnit>& units,
+                        std::vector<int32_t>& chunk_level_begin) {
+    build_chunk_stream_impl(events, preds, level_begin, n_levels, dense, units, chunk_level_begin);
+}
 
 bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& out, std::string& err) {
     out = HostPlan{};
@@ -512,7 +557,8 @@ bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& 
         out.orphans.push_back(pr);
     }
 
-    build_chunk_stream(out);
+    build_chunk_stream(out.events, out.preds, out.level_begin, out.n_levels, false, out.units, out.chunk_level_begin);
+    out.n_chunks = int32_t(out.units.size() / size_t(kChunkUnits));
 
     // reduced-mode scratch slots: a slot is released once the LEVEL of the value's last consumer
     // has completed, so warps that split a level never race on a recycled row.

@@ -47,6 +47,13 @@ struct HostPlan {
     int32_t n_slots = 0;
 };
 
+// Packs evaluation-ordered records into the chunk stream (mcdp_records.h); also used for the reduced mode's
+// slot-row variant of the records.  `dense`: no level alignment (for launches in which one warp walks the
+// whole stream in order); chunk_level_begin is then {0, n_chunks}.
+void build_chunk_stream(const std::vector<EventRec>& events, const std::vector<PredRec>& preds,
+                        const std::vector<int32_t>& level_begin, int32_t n_levels, bool dense, std::vector<ChunkUnit>& units,
+                        std::vector<int32_t>& chunk_level_begin);
+
 // Returns false and fills `err` (the reference's std::runtime_error texts where it has one).
 bool compile_plan(const mcdp_graph_desc& g, const mcdp_dists_desc& d, HostPlan& out, std::string& err);
 

@@ -80,7 +80,7 @@ struct alignas(16) HeaderUnit {
     uint32_t meta;           // kKindEvent << 29, or kKindEnd << 29 | 1 for a continuation header
     uint32_t remaining;      // continuation chunks that still follow this chunk's last event
     uint32_t first_src_row;  // chunk-opening header: source row of the chunk's first entry (else kNoRow)
-    uint32_t pad;
+    uint32_t pad;            // 1 = forward: the first entry's source is the event this warp closed just before
 };
 static_assert(sizeof(HeaderUnit) == 32, "HeaderUnit must be 32 bytes");
 union ChunkUnit {
