@@ -266,7 +266,7 @@ def run_b200(args):
     achieved = n * A * bpe / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "bytes_per_edge_sample": bpe,
-                "kernel": "mcdp::sweep_kernel", "avg_launch_ms": avg_launch_s * 1e3}
+                "kernel": "mcdp::chunk_sweep_kernel", "avg_launch_ms": avg_launch_s * 1e3}
     prof = os.path.join(ROOT, "profiles", f"traffic_{wl}.json")
     if os.path.exists(prof):
         try:
