@@ -169,3 +169,46 @@ def test_reduced_mode_matches_full_outputs():
         ref_hist = np.stack([np.bincount(bins[:, e], minlength=16) for e in range(plan.E)])
         assert np.array_equal(st.hist, ref_hist.astype(np.uint32))
         assert int(st.hist.sum()) == seeds.size * plan.E
+
+
+@pytest.mark.parametrize("seed0", [0, 4096, 7, -6])
+@pytest.mark.parametrize("wpg", [0, 1, 4])
+def test_device_call_with_seed0_equals_seed_array(seed0, wpg):
+    """mcdp_run_full_device / mcdp_run_reduced_device with seeds given as seed0 + column (the bench path; lanes own
+    seed pairs {2k, 2k+1} when seed0 is even) return exactly what the same seeds give as an explicit array, in an
+    order in which no lane owns a pair."""
+    import torch
+
+    dag, dists = synth.random_dag(400, 21), synth.mixed_small_dists()
+    plan = capi.Plan(dag, dists, device=0)
+    if wpg:
+        plan.set_option(capi.OPT_WARPS_PER_GROUP, wpg)
+    n, ld = 300, 320
+    E, A = plan.E, plan.A
+    dev = torch.device("cuda:0")
+    r = torch.zeros((E, ld), dtype=torch.float64, device=dev)
+    d = torch.zeros((A, ld), dtype=torch.float64, device=dev)
+    c = torch.zeros((E, ld), dtype=torch.int32, device=dev)
+    plan.run_full_device(n, r, d, c, ld, seed0=seed0)
+    torch.cuda.synchronize()
+    seeds = np.arange(seed0, seed0 + n, dtype=np.int32)
+    # reversed order: no lane owns a seed pair (one Philox block per sample instead of one per pair)
+    r_h, d_h, c_h = (x[::-1] for x in plan.run_many_host(seeds[::-1].copy()))
+    r_p, d_p, c_p = plan.run_many_host(seeds)  # in order: pairs wherever seed0 is even
+    assert np.array_equal(_bits(r_p), _bits(r_h)) and np.array_equal(_bits(d_p), _bits(d_h)) and np.array_equal(c_p, c_h)
+    assert np.array_equal(_bits(r[:, :n].T.cpu().numpy()), _bits(r_h))
+    assert np.array_equal(_bits(d[:, :n].T.cpu().numpy()), _bits(d_h))
+    assert np.array_equal(c[:, :n].T.cpu().numpy(), c_h)
+    # reduced statistics: integer accumulators exact, sums to summation order
+    desc = capi.make_stats_desc(thresholds=(1.0, 10.0), n_bins=16, hist_range=(0.0, 60.0))
+    s_sum = torch.zeros(E, dtype=torch.float64, device=dev)
+    s_sq = torch.zeros(E, dtype=torch.float64, device=dev)
+    s_late = torch.zeros((2, E), dtype=torch.int64, device=dev)
+    s_hist = torch.zeros((E, 16), dtype=torch.int32, device=dev)
+    plan.run_reduced_device(n, desc, s_sum, s_sq, s_late, s_hist, seed0=seed0)
+    torch.cuda.synchronize()
+    st = plan.run_reduced_host(seeds, thresholds=(1.0, 10.0), n_bins=16, hist_range=(0.0, 60.0))
+    assert np.array_equal(s_late.cpu().numpy().astype(np.uint64), np.asarray(st.late, dtype=np.uint64))
+    assert np.array_equal(s_hist.cpu().numpy().astype(np.uint32), np.asarray(st.hist, dtype=np.uint32))
+    assert np.allclose(s_sum.cpu().numpy(), st.sum, rtol=1e-12, atol=1e-9)
+    assert np.allclose(s_sq.cpu().numpy(), st.sumsq, rtol=1e-12, atol=1e-9)
