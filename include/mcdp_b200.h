@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MCDP_ABI_VERSION 1
+#define MCDP_ABI_VERSION 2 /* 2: + mcdp_run_attribution_device / _host (additive) */
 
 enum {
     MCDP_OK = 0,
@@ -151,6 +151,17 @@ int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t
                                 const mcdp_stats_desc* desc, double* d_sum, double* d_sumsq,
                                 unsigned long long* d_late, uint32_t* d_hist, void* stream);
 
+/* The same pass plus delay-cause attribution (replaces the np.bincount a caller runs over
+ * SimResult.cause_event joined with the precedence list): d_cause_act[A] (u64) counts the samples in which a
+ * precedence entry with that activity index decided realized[target] (_core.cpp:343-346: the last entry whose
+ * clamped arrival reached the running maximum), d_cause_none[E] (u64) those with cause_event == -1.  Entries
+ * whose activity index has no duration row (>= activity_count()) are not counted.  Both accumulate (+=); pass
+ * both or neither. */
+int32_t mcdp_run_attribution_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n,
+                                    const mcdp_stats_desc* desc, double* d_sum, double* d_sumsq,
+                                    unsigned long long* d_late, uint32_t* d_hist, unsigned long long* d_cause_act,
+                                    unsigned long long* d_cause_none, void* stream);
+
 /* [rows][ld] event-major -> [n][rows] sample-major (and back), for callers that hold device buffers. */
 int32_t mcdp_transpose_f64_device(const double* d_in, int64_t rows, int64_t n, int64_t ld, double* d_out, void* stream);
 int32_t mcdp_transpose_i32_device(const int32_t* d_in, int64_t rows, int64_t n, int64_t ld, int32_t* d_out, void* stream);
@@ -165,6 +176,10 @@ int32_t mcdp_run_many_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, dou
 int32_t mcdp_run_injected_host(mcdp_plan* plan, const double* durations, int64_t n, double* realized, int32_t* cause);
 int32_t mcdp_run_reduced_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, const mcdp_stats_desc* desc,
                               double* sum, double* sumsq, unsigned long long* late, uint32_t* hist);
+
+int32_t mcdp_run_attribution_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, const mcdp_stats_desc* desc,
+                                  double* sum, double* sumsq, unsigned long long* late, uint32_t* hist,
+                                  unsigned long long* cause_act, unsigned long long* cause_none);
 
 void* mcdp_host_alloc(size_t bytes); /* pinned host memory, NULL on failure */
 void mcdp_host_free(void* p);

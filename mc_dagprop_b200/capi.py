@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = (
     "mcdp_plan_level_count", "mcdp_plan_slot_count", "mcdp_plan_device", "mcdp_plan_get_order", "mcdp_plan_get_cumulative",
     "mcdp_run_full_device", "mcdp_run_injected_device", "mcdp_run_reduced_device", "mcdp_transpose_f64_device",
     "mcdp_transpose_i32_device", "mcdp_run_many_host", "mcdp_run_injected_host", "mcdp_run_reduced_host",
-    "mcdp_host_alloc", "mcdp_host_free",
+    "mcdp_run_attribution_device", "mcdp_run_attribution_host", "mcdp_host_alloc", "mcdp_host_free",
 )
 
 
@@ -89,6 +89,8 @@ def lib() -> C.CDLL:
         L.mcdp_run_many_host.argtypes = [vp, vp, i64, vp, vp, vp]
         L.mcdp_run_injected_host.argtypes = [vp, vp, i64, vp, vp]
         L.mcdp_run_reduced_host.argtypes = [vp, vp, i64, C.POINTER(StatsDesc), vp, vp, vp, vp]
+        L.mcdp_run_attribution_device.argtypes = [vp, vp, i32, i64, C.POINTER(StatsDesc), vp, vp, vp, vp, vp, vp, vp]
+        L.mcdp_run_attribution_host.argtypes = [vp, vp, i64, C.POINTER(StatsDesc), vp, vp, vp, vp, vp, vp]
         L.mcdp_host_alloc.argtypes = [C.c_size_t]
         L.mcdp_host_alloc.restype = vp
         L.mcdp_host_free.argtypes = [vp]
@@ -254,6 +256,20 @@ class Plan:
                                            q.ctypes.data, late.ctypes.data if late.size else None,
                                            hist.ctypes.data if hist.size else None))
         return Stats(seeds.size, s, q, late, hist, tuple(thresholds), tuple(hist_range))
+
+    def run_attribution_host(self, seeds, thresholds=(), n_bins=0, hist_range=(0.0, 1.0)):
+        """Statistics + delay-cause attribution: returns (Stats, cause_act[A] u64, cause_none[E] u64)."""
+        seeds = _np(seeds, np.int32)
+        desc = make_stats_desc(thresholds, n_bins, hist_range)
+        s, q = np.zeros(self.E, np.float64), np.zeros(self.E, np.float64)
+        late = np.zeros((len(thresholds), self.E), np.uint64)
+        hist = np.zeros((self.E, n_bins), np.uint32)
+        cause_act, cause_none = np.zeros(self.A, np.uint64), np.zeros(self.E, np.uint64)
+        _check(lib().mcdp_run_attribution_host(self._h, seeds.ctypes.data, seeds.size, C.byref(desc), s.ctypes.data,
+                                               q.ctypes.data, late.ctypes.data if late.size else None,
+                                               hist.ctypes.data if hist.size else None, cause_act.ctypes.data,
+                                               cause_none.ctypes.data))
+        return Stats(seeds.size, s, q, late, hist, tuple(thresholds), tuple(hist_range)), cause_act, cause_none
 
     # -- device-buffer calls (event-major [rows][ld]; torch tensors, addresses or None) --
     def run_full_device(self, n, realized, durations, cause, ld, seeds=None, seed0=0, stream=None):

@@ -191,12 +191,12 @@ struct LaunchShape {
 };
 
 // How many warps split a level, how many 64-sample groups share a CTA.
-LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false, int n_bins = 0) {
+LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false, int n_bins = 0, bool single_batch = false) {
     const HostPlan& h = plan->host;
     LaunchShape s{};
     int64_t n_groups = (n + 63) / 64;
     int batches = 1;
-    if (reduced) {
+    if (reduced && !single_batch) {
         // once there are more 64-sample batches than warp slots, fold several batches per group so the
         // global accumulators see one flush per event per group instead of one per 64 samples
         const int64_t slots = int64_t(plan->sm_count) * 32;
@@ -289,7 +289,7 @@ int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p_in, const LaunchShape
     {
         // chunk stream (mcdp_chunk_sweep.cuh): tables (128-byte rounded) + per-warp chunk ring.  One warp per
         // group walks the dense stream, several warps per group split the level-aligned one.
-        const int32_t rc = ensure_chunk_stream(plan, MODE == kModeReduced, s.wpg == 1, p);
+        const int32_t rc = ensure_chunk_stream(plan, MODE == kModeReduced || MODE == kModeAttr, s.wpg == 1, p);
         if (rc) return rc;
         const size_t bytes = size_t(p.n_chunks) * size_t(kChunkBytes);
         const size_t smem = ((s.smem + 127) & ~size_t(127)) + chunk_ring_bytes(s.threads / 32);
@@ -629,7 +629,16 @@ int32_t mcdp_run_injected_device(mcdp_plan* plan, const double* d_durations, int
 int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n,
                                 const mcdp_stats_desc* desc, double* d_sum, double* d_sumsq,
                                 unsigned long long* d_late, uint32_t* d_hist, void* stream) {
+    return mcdp_run_attribution_device(plan, d_seeds, seed0, n, desc, d_sum, d_sumsq, d_late, d_hist, nullptr, nullptr, stream);
+}
+
+int32_t mcdp_run_attribution_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n,
+                                    const mcdp_stats_desc* desc, double* d_sum, double* d_sumsq,
+                                    unsigned long long* d_late, uint32_t* d_hist, unsigned long long* d_cause_act,
+                                    unsigned long long* d_cause_none, void* stream) {
     if (!plan || !desc) return fail(MCDP_ERR_ARG, "null argument");
+    const bool attr = d_cause_act != nullptr || d_cause_none != nullptr;
+    if (attr && (!d_cause_act || !d_cause_none)) return fail(MCDP_ERR_ARG, "cause_act and cause_none go together");
     if (plan->device < 0) return fail(MCDP_ERR_CUDA, "plan was created host-only (MCDP_DEVICE_NONE): there is no CPU execution path");
     if (n < 0) return fail(MCDP_ERR_ARG, "n must be non-negative");
     if (plan->rng_stream == 1) return fail(MCDP_ERR_ARG, "the reference-compatible stream is available for full-output calls only");
@@ -654,8 +663,10 @@ int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t m = std::min(chunk, n - off);
-        const LaunchShape s = choose_shape(plan, m, true, d_hist ? desc->n_bins : 0);
+        const LaunchShape s = choose_shape(plan, m, true, d_hist ? desc->n_bins : 0, attr);
         SweepParams p = base_params(plan, s, m, chunk);
+        p.cause_act = d_cause_act;
+        p.cause_none = d_cause_none;
         p.events = plan->d_events_red.p;
         p.preds = plan->d_preds_red.p;
         p.seeds = d_seeds ? d_seeds + off : nullptr;
@@ -670,7 +681,7 @@ int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t
         p.n_bins = desc->n_bins;
         p.hist_lo = desc->hist_lo;
         p.hist_scale = desc->n_bins > 0 ? double(desc->n_bins) / (desc->hist_hi - desc->hist_lo) : 0.0;
-        rc = launch_sweep<kModeReduced>(plan, p, s, st);
+        rc = attr ? launch_sweep<kModeAttr>(plan, p, s, st) : launch_sweep<kModeReduced>(plan, p, s, st);
         if (rc) return rc;
     }
     return MCDP_OK;
@@ -827,21 +838,31 @@ int32_t mcdp_run_injected_host(mcdp_plan* plan, const double* durations, int64_t
 
 int32_t mcdp_run_reduced_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, const mcdp_stats_desc* desc,
                               double* sum, double* sumsq, unsigned long long* late, uint32_t* hist) {
+    return mcdp_run_attribution_host(plan, seeds, n, desc, sum, sumsq, late, hist, nullptr, nullptr);
+}
+
+int32_t mcdp_run_attribution_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, const mcdp_stats_desc* desc,
+                                  double* sum, double* sumsq, unsigned long long* late, uint32_t* hist,
+                                  unsigned long long* cause_act, unsigned long long* cause_none) {
     if (!plan || !desc) return fail(MCDP_ERR_ARG, "null argument");
     if (plan->device < 0) return fail(MCDP_ERR_CUDA, "plan was created host-only (MCDP_DEVICE_NONE): there is no CPU execution path");
     if (n > 0 && !seeds) return fail(MCDP_ERR_ARG, "null seeds");
-    const int64_t E = plan->host.E;
+    const bool attr = cause_act != nullptr || cause_none != nullptr;
+    if (attr && (!cause_act || !cause_none)) return fail(MCDP_ERR_ARG, "cause_act and cause_none go together");
+    const int64_t E = plan->host.E, A = plan->host.A;
     const int64_t nt = std::max(desc->n_thresholds, 0), nb = std::max(desc->n_bins, 0);
     double* d_sum = nullptr;
     double* d_sumsq = nullptr;
     unsigned long long* d_late = nullptr;
+    unsigned long long* d_cause_act = nullptr;
+    unsigned long long* d_cause_none = nullptr;
     uint32_t* d_hist = nullptr;
     int32_t* d_seeds = nullptr;
     {
         std::lock_guard<std::mutex> lock(plan->mu);
         DeviceGuard guard(plan->device);
         MCDP_CUDA(plan->d_stat_f64.ensure(size_t(2 * E)));
-        MCDP_CUDA(plan->d_stat_u64.ensure(size_t(nt * E)));
+        MCDP_CUDA(plan->d_stat_u64.ensure(size_t(nt * E) + (attr ? size_t(A + E) : 0)));
         MCDP_CUDA(plan->d_stat_u32.ensure(size_t(nb * E)));
         MCDP_CUDA(plan->slots[0].seeds.ensure(size_t(std::max<int64_t>(n, 1))));
         d_sum = plan->d_stat_f64.p;
@@ -852,10 +873,16 @@ int32_t mcdp_run_reduced_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, 
         MCDP_CUDA(cudaMemset(d_sum, 0, size_t(2 * E) * 8));
         if (nt) MCDP_CUDA(cudaMemset(d_late, 0, size_t(nt * E) * 8));
         if (nb) MCDP_CUDA(cudaMemset(d_hist, 0, size_t(nb * E) * 4));
+        if (attr) {
+            d_cause_act = d_late + nt * E;
+            d_cause_none = d_cause_act + A;
+            MCDP_CUDA(cudaMemset(d_cause_act, 0, size_t(A + E) * 8));
+        }
         if (n) MCDP_CUDA(cudaMemcpy(d_seeds, seeds, size_t(n) * 4, cudaMemcpyHostToDevice));
     }
-    int32_t rc = mcdp_run_reduced_device(plan, d_seeds, 0, n, desc, sum ? d_sum : nullptr, sumsq ? d_sumsq : nullptr,
-                                         late ? d_late : nullptr, hist ? d_hist : nullptr, nullptr);
+    int32_t rc = mcdp_run_attribution_device(plan, d_seeds, 0, n, desc, sum ? d_sum : nullptr, sumsq ? d_sumsq : nullptr,
+                                             late ? d_late : nullptr, hist ? d_hist : nullptr, d_cause_act, d_cause_none,
+                                             nullptr);
     if (rc) return rc;
     DeviceGuard guard(plan->device);
     MCDP_CUDA(cudaDeviceSynchronize());
@@ -863,6 +890,10 @@ int32_t mcdp_run_reduced_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, 
     if (sumsq) MCDP_CUDA(cudaMemcpy(sumsq, d_sumsq, size_t(E) * 8, cudaMemcpyDeviceToHost));
     if (late && nt) MCDP_CUDA(cudaMemcpy(late, d_late, size_t(nt * E) * 8, cudaMemcpyDeviceToHost));
     if (hist && nb) MCDP_CUDA(cudaMemcpy(hist, d_hist, size_t(nb * E) * 4, cudaMemcpyDeviceToHost));
+    if (attr) {
+        if (A) MCDP_CUDA(cudaMemcpy(cause_act, d_cause_act, size_t(A) * 8, cudaMemcpyDeviceToHost));
+        if (E) MCDP_CUDA(cudaMemcpy(cause_none, d_cause_none, size_t(E) * 8, cudaMemcpyDeviceToHost));
+    }
     return MCDP_OK;
 }
 

@@ -65,6 +65,7 @@ __host__ __device__ inline size_t chunk_ring_bytes(int n_warps) { return size_t(
 template <int MODE, bool SMEM, bool DYN>
 __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
     chunk_sweep_kernel(const __grid_constant__ SweepParams p) {
+    constexpr bool kReduced = MODE == kModeReduced || MODE == kModeAttr;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     // Dynamic shared memory: [log table][DistRec[] + table pool (SMEM)][per-warp chunk rings].  Everything
     // is addressed through ONE shared-window base register (kept opaque so that it is not re-derived
@@ -178,7 +179,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
             lat_a = ra;
             lat_b = rb;
         }
-        if constexpr (MODE != kModeReduced) {
+        if constexpr (!kReduced) {
             __stcs(reinterpret_cast<int2*>(i32_row(p.cause, row)), make_int2(cause_a, cause_b));
         } else {
             // per-event statistics of the delay realized - earliest over this warp's 64 samples: one
@@ -215,6 +216,21 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
                 const unsigned gb = __match_any_sync(0xFFFFFFFFu, bb);
                 if (bb >= 0 && lane == __ffs(gb) - 1) atomicAdd(h + bb, uint32_t(__popc(gb)));
             }
+            if constexpr (MODE == kModeAttr) {
+                // delay-cause attribution: cause_* hold the activity index of the entry that decided the event
+                // (-1 none, -3 an entry without a duration row); equal winners across the warp share one atomic
+                const int wa = valid_a ? cause_a : -4 - lane, wb = valid_b ? cause_b : -4 - lane;
+                const unsigned ga = __match_any_sync(0xFFFFFFFFu, wa);
+                if (lane == __ffs(ga) - 1) {
+                    if (wa >= 0) atomicAdd(p.cause_act + wa, (unsigned long long)__popc(ga));
+                    else if (wa == -1) atomicAdd(p.cause_none + ev, (unsigned long long)__popc(ga));
+                }
+                const unsigned gb = __match_any_sync(0xFFFFFFFFu, wb);
+                if (lane == __ffs(gb) - 1) {
+                    if (wb >= 0) atomicAdd(p.cause_act + wb, (unsigned long long)__popc(gb));
+                    else if (wb == -1) atomicAdd(p.cause_none + ev, (unsigned long long)__popc(gb));
+                }
+            }
         }
     };
     auto process = [&](uint32_t buf, int u0, uint32_t remaining) {
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
                 // _core.cpp:333-337
                 row = uint32_t(q0.x);
                 const double earliest = __hiloint2double(q0.w, q0.z);
-                if constexpr (MODE == kModeReduced) {
+                if constexpr (kReduced) {
                     ev = uint32_t(q0.y);
                     ev_earliest = earliest;
                 }
@@ -280,7 +296,8 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
             // _core.cpp:341-346
             const double ta = ref_min(__dadd_rn(rs.x, da), ub);
             const double tb = ref_min(__dadd_rn(rs.y, db), ub);
-            const int src_event = q0.x;
+            // what cause_event reports: the source event; in attribution mode the deciding entry's activity
+            const int src_event = MODE == kModeAttr ? (act == kNoAct ? -3 : int(act)) : q0.x;
             if (ta >= lat_a) {
                 lat_a = ta;
                 cause_a = src_event;

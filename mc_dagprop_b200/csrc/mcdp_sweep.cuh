@@ -24,7 +24,8 @@ namespace mcdp {
 #define MCDP_MIN_BLOCKS 2
 #endif
 
-enum SweepMode { kModeFull = 0, kModeInjected = 1, kModeReduced = 2 };
+// kModeAttr: reduced statistics + delay-cause attribution (per-activity counts of being the binding predecessor)
+enum SweepMode { kModeFull = 0, kModeInjected = 1, kModeReduced = 2, kModeAttr = 3 };
 
 struct SweepParams {
     const EventRec* events;
@@ -45,6 +46,8 @@ struct SweepParams {
     double* sumsq;
     unsigned long long* late;
     uint32_t* hist;
+    unsigned long long* cause_act;   // kModeAttr: [A] samples in which an entry with this activity decided its target
+    unsigned long long* cause_none;  // kModeAttr: [E] samples with cause_event == -1
     double thresholds[MCDP_MAX_THRESHOLDS];
     double hist_lo, hist_scale;
     double max_delay;

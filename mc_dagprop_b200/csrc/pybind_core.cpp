@@ -301,8 +301,9 @@ class MonteCarloPropagator {
 
     // additive: fused per-event statistics of realized - earliest
     py::dict run_many_reduced(py::array_t<int32_t, py::array::c_style | py::array::forcecast> seeds,
-                              std::vector<double> thresholds, int n_bins, double hist_lo, double hist_hi) {
-        const int64_t n = seeds.size(), E = node_count();
+                              std::vector<double> thresholds, int n_bins, double hist_lo, double hist_hi,
+                              bool cause_counts) {
+        const int64_t n = seeds.size(), E = node_count(), A = activity_count();
         if (thresholds.size() > MCDP_MAX_THRESHOLDS) throw std::runtime_error("at most 4 thresholds");
         mcdp_stats_desc desc{};
         desc.n_thresholds = int32_t(thresholds.size());
@@ -313,12 +314,16 @@ class MonteCarloPropagator {
         py::array_t<double> sum(E), sumsq(E);
         py::array_t<unsigned long long> late({int64_t(thresholds.size()), E});
         py::array_t<uint32_t> hist({E, int64_t(n_bins)});
+        // delay-cause attribution: how often each activity was the binding predecessor of its target event
+        py::array_t<unsigned long long> cause_act(cause_counts ? A : 0), cause_none(cause_counts ? E : 0);
         int32_t rc;
         {
             py::gil_scoped_release release;
-            rc = mcdp_run_reduced_host(plan_, seeds.data(), n, &desc, sum.mutable_data(), sumsq.mutable_data(),
-                                       late.size() ? late.mutable_data() : nullptr,
-                                       hist.size() ? hist.mutable_data() : nullptr);
+            rc = mcdp_run_attribution_host(plan_, seeds.data(), n, &desc, sum.mutable_data(), sumsq.mutable_data(),
+                                           late.size() ? late.mutable_data() : nullptr,
+                                           hist.size() ? hist.mutable_data() : nullptr,
+                                           cause_counts ? cause_act.mutable_data() : nullptr,
+                                           cause_counts ? cause_none.mutable_data() : nullptr);
         }
         if (rc != MCDP_OK) throw_last();
         py::dict out;
@@ -327,6 +332,10 @@ class MonteCarloPropagator {
         out["sumsq"] = sumsq;
         out["late"] = late;
         out["hist"] = hist;
+        if (cause_counts) {
+            out["cause_activity"] = cause_act;
+            out["cause_none"] = cause_none;
+        }
         return out;
     }
 };
@@ -494,5 +503,7 @@ PYBIND11_MODULE(_core, m) {
              "Propagate caller-supplied durations[n,A]; returns (realized[n,E], cause_event[n,E])")
         .def("run_many_reduced", &MonteCarloPropagator::run_many_reduced, py::arg("seeds"),
              py::arg("thresholds") = std::vector<double>{}, py::arg("n_bins") = 0, py::arg("hist_lo") = 0.0,
-             py::arg("hist_hi") = 1.0, "Per-event statistics of realized - earliest without materialising samples");
+             py::arg("hist_hi") = 1.0, py::arg("cause_counts") = false,
+             "Per-event statistics of realized - earliest without materialising samples; cause_counts adds "
+             "cause_activity[A] / cause_none[E]: how often each activity decided its target event / no predecessor did");
 }

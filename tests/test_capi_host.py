@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = capi.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mcdp_abi_version() == 1
+    assert lib.mcdp_abi_version() == 2
 
 
 def test_no_cpu_execution_path():

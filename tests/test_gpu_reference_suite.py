@@ -278,6 +278,13 @@ def test_additive_array_api_agrees_with_sim_results(fixture_ctx):
     earliest = np.array([0.0, 5.0, 10.0, 22.0, 20.0, 100.0])
     np.testing.assert_allclose(st["sum"], (r - earliest).sum(0), rtol=1e-12, atol=1e-9)
     assert st["hist"].sum() == 50 * 6 and np.array_equal(st["late"][0], ((r - earliest) > 1.0).sum(0))
+    # delay-cause attribution through the Python surface: one activity per precedence entry in this fixture, so
+    # the per-activity counts are the bincount of cause_event per target
+    sa = sim.run_many_reduced(seeds, cause_counts=True)
+    assert np.array_equal(sa["cause_none"], (c == -1).sum(0))
+    for tgt, preds in fixture_ctx[2]:
+        for src, act in preds:
+            assert sa["cause_activity"][act] == np.count_nonzero(c[:, tgt] == src)
     # array ingest builds the same propagator
     from mc_dagprop_b200.flat import FlatDag
     fd = FlatDag.from_precedence_list(earliest, [(0, 3.0, 1), (1, 5.0, 1), (2, 5.0, 1), (3, 15.0, 2), (4, 10.0, 3)],

@@ -112,3 +112,54 @@ def test_tier3_per_event_quantiles(gen):
         worst = max(worst, float(np.max(np.maximum(lo - hi_ref, lo_ref - hi))))
         assert not bad.any(), (gen, q, int(bad.sum()))
     assert worst < 0.05
+
+
+def _expected_cause_counts(dag, realized, durations):
+    """Replays _core.cpp:332-350 on given realized / durations samples and counts, per activity, how often its
+    precedence entry decided the target event (the last entry whose clamped arrival reached the running maximum)."""
+    n, E = realized.shape
+    A = durations.shape[1]
+    cause_act = np.zeros(A, np.uint64)
+    cause_none = np.zeros(E, np.uint64)
+    entry_of = {}
+    for i, t in enumerate(dag.prec_target):  # the last entry for a target wins (_core.cpp:240)
+        entry_of[int(t)] = i
+    for e in range(E):
+        ub = dag.earliest[e] + dag.max_delay
+        latest = np.full(n, dag.earliest[e])
+        win = np.full(n, -1, np.int64)
+        i = entry_of.get(e)
+        if i is not None:
+            for k in range(dag.prec_off[i], dag.prec_off[i + 1]):
+                src, act = int(dag.pred_src[k]), int(dag.pred_act[k])
+                dur = durations[:, act] if act < A else 0.0
+                t = np.minimum(realized[:, src] + dur, ub)
+                take = t >= latest
+                latest = np.where(take, t, latest)
+                win = np.where(take, act if act < A else -3, win)
+        assert np.array_equal(np.minimum(latest, ub).view(np.uint64), realized[:, e].copy().view(np.uint64))
+        cause_none[e] = np.count_nonzero(win == -1)
+        acts, counts = np.unique(win[win >= 0], return_counts=True)
+        cause_act[acts] += counts.astype(np.uint64)
+    return cause_act, cause_none
+
+
+@pytest.mark.parametrize("wpg", [0, 1])
+def test_delay_cause_attribution_counts(wpg):
+    """mcdp_run_attribution_host: per-activity counts of being the binding predecessor equal the counts derived
+    from the full outputs of the same seeds, exactly; the other statistics are those of the plain reduced call."""
+    dag, dists = synth.random_dag(250, 5, max_delay=40.0), synth.mixed_small_dists()
+    plan = capi.Plan(dag, dists, device=0)
+    if wpg:
+        plan.set_option(capi.OPT_WARPS_PER_GROUP, wpg)
+    seeds = np.arange(3, 3 + 1000, dtype=np.int32)
+    r, d, c = plan.run_many_host(seeds)
+    exp_act, exp_none = _expected_cause_counts(dag, r, d)
+    assert np.array_equal(exp_none, (c == -1).sum(0).astype(np.uint64))
+    st, cause_act, cause_none = plan.run_attribution_host(seeds, thresholds=(1.0,), n_bins=8, hist_range=(0.0, 40.0))
+    assert np.array_equal(cause_act, exp_act)
+    assert np.array_equal(cause_none, exp_none)
+    assert int(cause_act.sum() + cause_none.sum()) <= seeds.size * plan.E
+    ref = plan.run_reduced_host(seeds, thresholds=(1.0,), n_bins=8, hist_range=(0.0, 40.0))
+    assert np.array_equal(st.late, ref.late) and np.array_equal(st.hist, ref.hist)
+    assert np.allclose(st.sum, ref.sum, rtol=1e-12, atol=1e-9)
