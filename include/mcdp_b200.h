@@ -132,6 +132,15 @@ int32_t mcdp_plan_get_order(const mcdp_plan* plan, int32_t* order_out, int32_t* 
 /* cumulative table the device searches for activity_type (== std::discrete_distribution's _M_cp); returns length or -1 */
 int64_t mcdp_plan_get_cumulative(const mcdp_plan* plan, int32_t activity_type, double* cp_out, int64_t cap);
 
+/* The chunk stream the sweep kernel walks (introspection for tests and tooling; layout: csrc/mcdp_records.h,
+ * 32-byte units, MCDP_CHUNK_UNITS per chunk).  rows: 0 = event ids (full / injected modes), 1 = recycled scratch
+ * slots (reduced modes); dense: 0 = level-aligned chunks (several warps per group), 1 = no level alignment (one warp
+ * per group).  Returns the number of chunks; copies min(n_chunks * 512, cap_bytes) bytes to units_out and, when not
+ * NULL, level_count + 1 chunk positions (dense: 2) to chunk_level_begin_out.  Works on host-only plans. */
+#define MCDP_CHUNK_UNITS 16
+int64_t mcdp_plan_get_chunks(const mcdp_plan* plan, int32_t rows, int32_t dense, void* units_out, int64_t cap_bytes,
+                             int32_t* chunk_level_begin_out);
+
 /* ---- device-buffer entry points (asynchronous on `stream`, a cudaStream_t passed as void*) ----
  * Seeds: d_seeds[n] (device) or, when d_seeds is NULL, the arithmetic run seed0, seed0+1, ... */
 

@@ -20,6 +20,11 @@ DEVICE_NONE = -1
 OPT_STREAM_KEY, OPT_WARPS_PER_GROUP, OPT_GROUPS_PER_CTA, OPT_HOST_CHUNK, OPT_RNG_STREAM = 0, 1, 2, 3, 4
 RNG_PHILOX, RNG_REFERENCE = 0, 1
 MAX_THRESHOLDS = 4
+CHUNK_UNITS = 16
+KIND_NONE, KIND_EVENT, KIND_END, NO_ROW, NO_ACT = 5, 6, 7, 0xFFFFFFFF, 0xFFFFFFFF
+#: one 32-byte unit of the chunk stream, viewed as a precedence entry (csrc/mcdp_records.h: PredRec); an event header
+#: (HeaderUnit) reads a = row, b = event id, x = earliest, meta, c = remaining, nxt = first_src_row, d = forward flag
+UNIT_DTYPE = np.dtype([("a", "<u4"), ("b", "<u4"), ("x", "<f8"), ("meta", "<u4"), ("c", "<u4"), ("nxt", "<u4"), ("d", "<u4")])
 
 #: every symbol include/mcdp_b200.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = (
@@ -28,7 +33,7 @@ EXPORTED_SYMBOLS = (
     "mcdp_plan_level_count", "mcdp_plan_slot_count", "mcdp_plan_device", "mcdp_plan_get_order", "mcdp_plan_get_cumulative",
     "mcdp_run_full_device", "mcdp_run_injected_device", "mcdp_run_reduced_device", "mcdp_transpose_f64_device",
     "mcdp_transpose_i32_device", "mcdp_run_many_host", "mcdp_run_injected_host", "mcdp_run_reduced_host",
-    "mcdp_run_attribution_device", "mcdp_run_attribution_host", "mcdp_host_alloc", "mcdp_host_free",
+    "mcdp_plan_get_chunks", "mcdp_run_attribution_device", "mcdp_run_attribution_host", "mcdp_host_alloc", "mcdp_host_free",
 )
 
 
@@ -81,6 +86,8 @@ def lib() -> C.CDLL:
         L.mcdp_plan_get_order.argtypes = [vp, vp, vp]
         L.mcdp_plan_get_cumulative.argtypes = [vp, i32, vp, i64]
         L.mcdp_plan_get_cumulative.restype = i64
+        L.mcdp_plan_get_chunks.argtypes = [vp, i32, i32, vp, i64, vp]
+        L.mcdp_plan_get_chunks.restype = i64
         L.mcdp_run_full_device.argtypes = [vp, vp, i32, i64, vp, vp, vp, i64, vp]
         L.mcdp_run_injected_device.argtypes = [vp, vp, i64, vp, vp, i64, vp]
         L.mcdp_run_reduced_device.argtypes = [vp, vp, i32, i64, C.POINTER(StatsDesc), vp, vp, vp, vp, vp]
@@ -215,6 +222,16 @@ class Plan:
         o, lv = np.empty(max(self.E, 1), np.int32), np.empty(max(self.E, 1), np.int32)
         _check(lib().mcdp_plan_get_order(self._h, o.ctypes.data, lv.ctypes.data))
         return o[: self.E], lv[: self.E]
+
+    def chunks(self, rows: int = 0, dense: bool = False):
+        """The chunk stream the sweep kernel walks: (units[n_chunks, 16] structured array, chunk_level_begin)."""
+        n_levels = 1 if dense else self.n_levels
+        clb = np.zeros(n_levels + 1, np.int32)
+        n = int(lib().mcdp_plan_get_chunks(self._h, int(rows), int(bool(dense)), None, 0, None))
+        raw = np.zeros(max(n, 0) * CHUNK_UNITS * 32, np.uint8)
+        lib().mcdp_plan_get_chunks(self._h, int(rows), int(bool(dense)), raw.ctypes.data if raw.size else None, raw.size,
+                                   clb.ctypes.data)
+        return raw.view(UNIT_DTYPE).reshape(n, CHUNK_UNITS), clb
 
     def cumulative(self, activity_type: int, cap: int = 1 << 20):
         out = np.empty(cap, np.float64)

@@ -17,6 +17,8 @@
 
 using namespace mcdp;
 
+static_assert(MCDP_CHUNK_UNITS == kChunkUnits, "header and records disagree on the chunk size");
+
 namespace {
 
 thread_local std::string g_err;
@@ -577,6 +579,25 @@ int64_t mcdp_plan_get_cumulative(const mcdp_plan* plan, int32_t activity_type, d
         return d.tab_len;
     }
     return -1;
+}
+
+int64_t mcdp_plan_get_chunks(const mcdp_plan* plan, int32_t rows, int32_t dense, void* units_out, int64_t cap_bytes,
+                             int32_t* chunk_level_begin_out) {
+    if (!plan) return -1;
+    const HostPlan& h = plan->host;
+    std::vector<EventRec> ev = h.events;
+    std::vector<PredRec> pr = h.preds;
+    if (rows) {  // scratch-slot rows, as ensure_reduced_stream builds them
+        for (auto& q : pr) q.src_row = h.slot_of_event[q.src_row];
+        for (auto& e : ev) e.row = h.slot_of_event[e.event];
+    }
+    std::vector<ChunkUnit> units;
+    std::vector<int32_t> clb;
+    build_chunk_stream(ev, pr, h.level_begin, h.n_levels, dense != 0, units, clb);
+    const int64_t bytes = int64_t(units.size() * sizeof(ChunkUnit));
+    if (units_out && cap_bytes > 0) std::memcpy(units_out, units.data(), size_t(std::min(bytes, cap_bytes)));
+    if (chunk_level_begin_out) std::copy(clb.begin(), clb.end(), chunk_level_begin_out);
+    return int64_t(units.size() / size_t(kChunkUnits));
 }
 
 int32_t mcdp_run_full_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n, double* d_realized,

@@ -68,10 +68,7 @@ __host__ __device__ inline uint32_t guide_doubles(uint32_t guide_log2) {
 // warp that is handed a continuation chunk by the level cursor skips it.
 // Precedence-entry units are PredRec as is; `next_src_row` names the source row of the next entry
 // unit the same warp will process (next event of the chunk included), kNoRow when there is none.
-#ifndef MCDP_CHUNK_UNITS
-#define MCDP_CHUNK_UNITS 16
-#endif
-constexpr int kChunkUnits = MCDP_CHUNK_UNITS;
+constexpr int kChunkUnits = 16;
 constexpr int kChunkBytes = kChunkUnits * 32;
 struct alignas(16) HeaderUnit {
     uint32_t row;            // realized / cause row of the event
