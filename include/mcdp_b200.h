@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define MCDP_ABI_VERSION 2 /* 2: + mcdp_run_attribution_device / _host (additive) */
+#define MCDP_ABI_VERSION 3 /* 2: + mcdp_run_attribution_device / _host; 3: + mcdp_plan_launch_shape,
+                              MCDP_OPT_SAMPLES_PER_LANE (both additive) */
 
 enum {
     MCDP_OK = 0,
@@ -104,9 +105,12 @@ enum {
     MCDP_OPT_WARPS_PER_GROUP = 1, /* warps that share one 64-sample group and split each topological level; 0 = auto */
     MCDP_OPT_GROUPS_PER_CTA = 2,  /* 64-sample groups per CTA; 0 = auto */
     MCDP_OPT_HOST_CHUNK = 3,      /* samples per device chunk in the *_host calls; 0 = auto from free HBM */
-    MCDP_OPT_RNG_STREAM = 4       /* 0 = Philox contract (default); 1 = reference-compatible stream: Xoshiro256++
+    MCDP_OPT_RNG_STREAM = 4,      /* 0 = Philox contract (default); 1 = reference-compatible stream: Xoshiro256++
                                      in activity-index order with the libstdc++ transforms (_core.cpp:313-329),
                                      full-output calls only, at most 64 distributions */
+    MCDP_OPT_SAMPLES_PER_LANE = 5 /* samples a lane owns in the sweep kernel: 2 = 64-sample groups at 64 registers,
+                                     4 = 128-sample groups at 128 registers with 256-bit row accesses (needs 32-byte
+                                     aligned buffers, else falls back to 2); 0 = auto.  Results do not depend on it. */
 };
 
 const char* mcdp_last_error(void);
@@ -140,6 +144,12 @@ int64_t mcdp_plan_get_cumulative(const mcdp_plan* plan, int32_t activity_type, d
 #define MCDP_CHUNK_UNITS 16
 int64_t mcdp_plan_get_chunks(const mcdp_plan* plan, int32_t rows, int32_t dense, void* units_out, int64_t cap_bytes,
                              int32_t* chunk_level_begin_out);
+
+/* The launch shape a call over n samples would take (introspection for tests, tooling and the benchmark's
+ * kernel label; works on host-only plans, which assume 148 SMs).  out8 = {samples per lane (2 pair kernel, 4 quad
+ * kernel), warps per group, groups per CTA, threads per CTA, grid size, dynamic shared memory bytes, 64-sample
+ * batches folded per group (reduced mode), 1 if the tables are staged in shared memory}. */
+int32_t mcdp_plan_launch_shape(const mcdp_plan* plan, int64_t n, int32_t reduced, int32_t n_bins, int64_t* out8);
 
 /* ---- device-buffer entry points (asynchronous on `stream`, a cudaStream_t passed as void*) ----
  * Seeds: d_seeds[n] (device) or, when d_seeds is NULL, the arithmetic run seed0, seed0+1, ... */

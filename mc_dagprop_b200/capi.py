@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_PKG, "libmcdp_b200.so")
 
 MCDP_OK, MCDP_ERR_INVALID, MCDP_ERR_CUDA, MCDP_ERR_ARG = 0, 1, 2, 3
 DEVICE_NONE = -1
-OPT_STREAM_KEY, OPT_WARPS_PER_GROUP, OPT_GROUPS_PER_CTA, OPT_HOST_CHUNK, OPT_RNG_STREAM = 0, 1, 2, 3, 4
+OPT_STREAM_KEY, OPT_WARPS_PER_GROUP, OPT_GROUPS_PER_CTA, OPT_HOST_CHUNK, OPT_RNG_STREAM, OPT_SAMPLES_PER_LANE = 0, 1, 2, 3, 4, 5
 RNG_PHILOX, RNG_REFERENCE = 0, 1
 MAX_THRESHOLDS = 4
 CHUNK_UNITS = 16
@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = (
     "mcdp_plan_level_count", "mcdp_plan_slot_count", "mcdp_plan_device", "mcdp_plan_get_order", "mcdp_plan_get_cumulative",
     "mcdp_run_full_device", "mcdp_run_injected_device", "mcdp_run_reduced_device", "mcdp_transpose_f64_device",
     "mcdp_transpose_i32_device", "mcdp_run_many_host", "mcdp_run_injected_host", "mcdp_run_reduced_host",
-    "mcdp_plan_get_chunks", "mcdp_run_attribution_device", "mcdp_run_attribution_host", "mcdp_host_alloc", "mcdp_host_free",
+    "mcdp_plan_get_chunks", "mcdp_plan_launch_shape", "mcdp_run_attribution_device", "mcdp_run_attribution_host", "mcdp_host_alloc", "mcdp_host_free",
 )
 
 
@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
         L.mcdp_plan_get_cumulative.restype = i64
         L.mcdp_plan_get_chunks.argtypes = [vp, i32, i32, vp, i64, vp]
         L.mcdp_plan_get_chunks.restype = i64
+        L.mcdp_plan_launch_shape.argtypes = [vp, i64, i32, i32, vp]
         L.mcdp_run_full_device.argtypes = [vp, vp, i32, i64, vp, vp, vp, i64, vp]
         L.mcdp_run_injected_device.argtypes = [vp, vp, i64, vp, vp, i64, vp]
         L.mcdp_run_reduced_device.argtypes = [vp, vp, i32, i64, C.POINTER(StatsDesc), vp, vp, vp, vp, vp]
@@ -237,6 +238,13 @@ class Plan:
         out = np.empty(cap, np.float64)
         n = lib().mcdp_plan_get_cumulative(self._h, int(activity_type), out.ctypes.data, cap)
         return None if n < 0 else out[:n].copy()
+
+    def launch_shape(self, n: int, reduced: bool = False, n_bins: int = 0) -> dict:
+        """The launch a call over n samples would take (which kernel, CTA shape); works on host-only plans."""
+        out = np.zeros(8, np.int64)
+        _check(lib().mcdp_plan_launch_shape(self._h, int(n), int(bool(reduced)), int(n_bins), out.ctypes.data))
+        keys = ("samples_per_lane", "warps_per_group", "groups_per_cta", "threads", "grid", "smem_bytes", "batches", "smem_tables")
+        return dict(zip(keys, out.tolist()))
 
     def set_option(self, option: int, value: int) -> None:
         _check(lib().mcdp_plan_set_option(self._h, option, int(value)))

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -14,6 +15,7 @@
 #include "mcdp_plan.hpp"
 #include "mcdp_compat.cuh"
 #include "mcdp_chunk_sweep.cuh"
+#include "mcdp_quad_sweep.cuh"
 
 using namespace mcdp;
 
@@ -129,6 +131,7 @@ struct mcdp_plan {
     // options
     uint32_t stream_key = 0;
     int warps_per_group = 0, groups_per_cta = 0;
+    int samples_per_lane = 0;  // 0 auto, 2 pair kernel (mcdp_chunk_sweep.cuh), 4 quad kernel (mcdp_quad_sweep.cuh)
     int64_t host_chunk = 0;
     int rng_stream = 0;  // 0 Philox contract, 1 reference-compatible Xoshiro stream
     DevBuf<ActRec> d_acts;
@@ -190,12 +193,23 @@ struct LaunchShape {
     unsigned grid;
     size_t smem;
     bool smem_tables;
+    int spl;  // samples per lane: 2 = pair kernel (64-sample groups), 4 = quad kernel (128-sample groups)
+    // what the shape was chosen for (launch_sweep re-chooses with spl = 2 when the buffers are not 32-byte aligned)
+    bool reduced, single_batch;
+    int n_bins;
 };
 
-// How many warps split a level, how many 64-sample groups share a CTA.
-LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false, int n_bins = 0, bool single_batch = false) {
+// Which kernel "auto" means.  Measured on B200 (profiles/r01_quad_ab.txt): see DESIGN.md section 5.
+constexpr int kAutoSamplesPerLane = MCDP_AUTO_SPL;
+
+// How many warps split a level, how many sample groups share a CTA, which kernel runs them.
+LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false, int n_bins = 0, bool single_batch = false,
+                         int force_spl = 0) {
     const HostPlan& h = plan->host;
     LaunchShape s{};
+    s.reduced = reduced;
+    s.single_batch = single_batch;
+    s.n_bins = n_bins;
     int64_t n_groups = (n + 63) / 64;
     int batches = 1;
     if (reduced && !single_batch) {
@@ -205,6 +219,12 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false,
         batches = int(std::max<int64_t>(1, std::min<int64_t>(64, n_groups / slots)));
         n_groups = (n_groups + batches - 1) / batches;
     }
+    // the quad kernel covers everything but the multi-batch reduced launches (mcdp_sweep.cuh)
+    int spl = force_spl ? force_spl : (plan->samples_per_lane ? plan->samples_per_lane : kAutoSamplesPerLane);
+    if (batches > 1) spl = 2;
+    s.spl = spl;
+    const int sm_warps = spl == 4 ? 16 : 32;  // resident warps per SM: 128 vs 64 registers per thread
+    if (spl == 4) n_groups = (n + kQuadSamples - 1) / kQuadSamples;
     int wpg = plan->warps_per_group;
     constexpr int kMaxWarps = MCDP_MAX_THREADS / 32;
     int gpc = plan->groups_per_cta;
@@ -219,10 +239,10 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false,
         for (int cand = 1; cand <= kMaxWarps && cand <= by_width; cand *= 2) {
             const int g = gpc > 0 ? std::min(gpc, kMaxWarps / cand) : std::max(1, 8 / cand);
             const int64_t ctas = (n_groups + g - 1) / g;
-            const int64_t per_sm = std::max(1, 32 / (cand * g));
+            const int64_t per_sm = std::max(1, sm_warps / (cand * g));
             const int64_t slots = int64_t(plan->sm_count) * per_sm;
             const int64_t waves = (ctas + slots - 1) / slots;
-            const double eff = double(n_groups * cand) / double(waves * plan->sm_count * 32);
+            const double eff = double(n_groups * cand) / double(waves * plan->sm_count * sm_warps);
             if (eff >= best - 1e-9) {
                 best = eff;
                 wpg = cand;
@@ -277,10 +297,25 @@ int32_t launch_kernel(mcdp_plan* plan, K k, const SweepParams& p, const LaunchSh
 
 int32_t ensure_chunk_stream(mcdp_plan* plan, bool reduced, bool dense, SweepParams& p);
 
+// the launch-shape dependent fields of the parameter block
+void apply_shape(SweepParams& p, const LaunchShape& s) {
+    p.smem_ring_off = uint32_t((s.smem + 127) & ~size_t(127));
+    p.warps_per_group = s.wpg;
+    p.batches_per_group = s.batches;
+}
+
+bool aligned32(const void* a) { return (reinterpret_cast<uintptr_t>(a) & 31) == 0; }
+
 template <int MODE>
-int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p_in, const LaunchShape& s, cudaStream_t stream) {
+int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p_in, const LaunchShape& s_in, cudaStream_t stream) {
     if (p_in.n <= 0) return MCDP_OK;
     SweepParams p = p_in;
+    LaunchShape s = s_in;
+    if (s.spl == 4 && !(aligned32(p.realized) && aligned32(p.durations) && aligned32(p.inj))) {
+        // the quad kernel moves 256-bit row segments: caller buffers that are only 16-byte aligned take the pair kernel
+        s = choose_shape(plan, p.n, s.reduced, s.n_bins, s.single_batch, 2);
+        apply_shape(p, s);
+    }
     if constexpr (MODE == kModeReduced) {
         // event + precedence record streams (mcdp_sweep.cuh)
         const size_t bytes = size_t(plan->host.E) * sizeof(EventRec) + size_t(plan->host.P) * sizeof(PredRec);
@@ -295,6 +330,13 @@ int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p_in, const LaunchShape
         if (rc) return rc;
         const size_t bytes = size_t(p.n_chunks) * size_t(kChunkBytes);
         const size_t smem = ((s.smem + 127) & ~size_t(127)) + chunk_ring_bytes(s.threads / 32);
+        if (s.spl == 4) {
+            if (s.wpg > 1)
+                return s.smem_tables ? launch_kernel(plan, quad_sweep_kernel<MODE, true, true>, p, s, smem, p.chunks, bytes, stream)
+                                     : launch_kernel(plan, quad_sweep_kernel<MODE, false, true>, p, s, smem, p.chunks, bytes, stream);
+            return s.smem_tables ? launch_kernel(plan, quad_sweep_kernel<MODE, true, false>, p, s, smem, p.chunks, bytes, stream)
+                                 : launch_kernel(plan, quad_sweep_kernel<MODE, false, false>, p, s, smem, p.chunks, bytes, stream);
+        }
         if (s.wpg > 1)
             return s.smem_tables ? launch_kernel(plan, chunk_sweep_kernel<MODE, true, true>, p, s, smem, p.chunks, bytes, stream)
                                  : launch_kernel(plan, chunk_sweep_kernel<MODE, false, true>, p, s, smem, p.chunks, bytes, stream);
@@ -316,7 +358,6 @@ SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, 
     p.ldb8 = uint32_t(ld) * 8u;
     p.ldb4 = uint32_t(ld) * 4u;
     p.smem_tab_off = uint32_t(kLogTabBytes + sizeof(DistRec) * h.dists.size());
-    p.smem_ring_off = uint32_t((s.smem + 127) & ~size_t(127));
     p.n_levels = h.n_levels;
     p.n_orphans = int32_t(h.orphans.size());
     p.n_dists = int32_t(h.dists.size());
@@ -325,8 +366,7 @@ SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, 
     p.last_pred = h.P > 0 ? uint32_t(h.P - 1) : 0u;
     p.max_delay = h.max_delay;
     for (int r = 0; r < 10; ++r) p.keys.k[r] = plan->stream_key + uint32_t(r) * 0x9E3779B9u;
-    p.warps_per_group = s.wpg;
-    p.batches_per_group = s.batches;
+    apply_shape(p, s);
     return p;
 }
 
@@ -486,6 +526,10 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
         return fail(MCDP_ERR_ARG, "device ordinal out of range");
     }
     plan->device = device;
+    if (const char* e = std::getenv("MCDP_SAMPLES_PER_LANE")) {  // process-wide default (A/B runs of whole test suites)
+        const int v = std::atoi(e);
+        if (v == 2 || v == 4) plan->samples_per_lane = v;
+    }
     DeviceGuard guard(device);
     if (!guard.ok) {
         delete plan;
@@ -543,6 +587,10 @@ int32_t mcdp_plan_set_option(mcdp_plan* plan, int32_t option, int64_t value) {
                 return fail(MCDP_ERR_ARG, "the reference-compatible stream supports at most 64 distributions");
             plan->rng_stream = int(value);
             break;
+        case MCDP_OPT_SAMPLES_PER_LANE:
+            if (value != 0 && value != 2 && value != 4) return fail(MCDP_ERR_ARG, "samples per lane must be 0 (auto), 2 or 4");
+            plan->samples_per_lane = int(value);
+            break;
         case MCDP_OPT_HOST_CHUNK:
             if (value < 0) return fail(MCDP_ERR_ARG, "host chunk must be non-negative");
             plan->host_chunk = value;
@@ -598,6 +646,21 @@ int64_t mcdp_plan_get_chunks(const mcdp_plan* plan, int32_t rows, int32_t dense,
     if (units_out && cap_bytes > 0) std::memcpy(units_out, units.data(), size_t(std::min(bytes, cap_bytes)));
     if (chunk_level_begin_out) std::copy(clb.begin(), clb.end(), chunk_level_begin_out);
     return int64_t(units.size() / size_t(kChunkUnits));
+}
+
+int32_t mcdp_plan_launch_shape(const mcdp_plan* plan, int64_t n, int32_t reduced, int32_t n_bins, int64_t* out8) {
+    if (!plan || !out8) return fail(MCDP_ERR_ARG, "null argument");
+    if (n < 0) return fail(MCDP_ERR_ARG, "n must be non-negative");
+    const LaunchShape s = choose_shape(plan, n, reduced != 0, n_bins);
+    out8[0] = s.spl;
+    out8[1] = s.wpg;
+    out8[2] = s.gpc;
+    out8[3] = s.threads;
+    out8[4] = int64_t(s.grid);
+    out8[5] = int64_t(s.batches > 1 ? s.smem : ((s.smem + 127) & ~size_t(127)) + chunk_ring_bytes(s.threads / 32));
+    out8[6] = s.batches;
+    out8[7] = s.smem_tables ? 1 : 0;
+    return MCDP_OK;
 }
 
 int32_t mcdp_run_full_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n, double* d_realized,

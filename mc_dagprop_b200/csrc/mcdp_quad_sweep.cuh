@@ -1,0 +1,366 @@
+// mcdp_quad_sweep.cuh -- the chunk-stream sweep of mcdp_chunk_sweep.cuh with FOUR samples per lane, sm_100a.
+//
+// Replaces Simulator::run (reference _core.cpp:312-353) for a block of seeds, like the pair kernel.
+// Same chunk stream, same ring, same level cursor; what differs:
+//   * a warp owns 128 adjacent samples, four per lane, so every predecessor read and every
+//     realized / duration write is ONE 256-bit access per lane (ld/st.global.v4.f64, sm_100) and a
+//     1 KB contiguous row segment per warp; cause_event rows are 128-bit stores;
+//   * the warp-uniform work of a stream unit -- record words, kind dispatch, distribution-record
+//     loads, row address arithmetic, loop control -- is paid once per 128 edge-samples instead of
+//     once per 64, and four independent dependency chains per lane are in flight;
+//   * one CTA of up to 16 warps per SM at 128 registers: the register file no longer shapes the
+//     loop body (the pair kernel sits at the 64-register spill edge).
+// Results are bit-identical to the pair kernel (same generator contract, same recurrence).
+#pragma once
+#include "mcdp_chunk_sweep.cuh"
+#include "mcdp_sampling4.cuh"
+
+namespace mcdp {
+
+struct D4 {
+    double x, y, z, w;
+};
+// 256-bit global accesses (PTX ISA 8.8, sm_100+): 32-byte aligned addresses
+__device__ __forceinline__ D4 ldcg_d4(const void* ptr) {  // L2 only: rows written by other warps
+    D4 v;
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(ptr));
+    return v;
+}
+__device__ __forceinline__ D4 ldcs_d4(const void* ptr) {  // streamed once
+    D4 v;
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(ptr));
+    return v;
+}
+__device__ __forceinline__ void stcg_d4(void* ptr, const D4& v) {
+    asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ void stcs_d4(void* ptr, const D4& v) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(ptr), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+
+constexpr int kQuadSamples = 128;  // samples per group
+
+// what MCDP_OPT_SAMPLES_PER_LANE = 0 (auto) selects
+#ifndef MCDP_AUTO_SPL
+#define MCDP_AUTO_SPL 2
+#endif
+
+template <int MODE, bool SMEM, bool DYN>
+__global__ void __launch_bounds__(MCDP_MAX_THREADS, 1) quad_sweep_kernel(const __grid_constant__ SweepParams p) {
+    constexpr bool kReduced = MODE == kModeReduced || MODE == kModeAttr;
+    extern __shared__ __align__(128) unsigned char smem_dyn[];
+    // dynamic shared memory as in chunk_sweep_kernel: [log table][DistRec[] + table pool (SMEM)][per-warp chunk rings]
+    uint32_t smem_base = smem_u32(smem_dyn);
+    asm volatile("" : "+r"(smem_base));
+    for (int i = threadIdx.x; i < kLogTabEntries; i += blockDim.x)
+        reinterpret_cast<int4*>(smem_dyn)[i] = __ldg(reinterpret_cast<const int4*>(p.log_tab) + i);
+    const uint32_t log_tab = smem_base;
+    typename Mem<SMEM>::ptr dists, tab;
+    if constexpr (SMEM) {
+        int4* s_dists = reinterpret_cast<int4*>(smem_dyn + kLogTabBytes);
+        double* s_tab = reinterpret_cast<double*>(smem_dyn + p.smem_tab_off);
+        const int n16 = int(sizeof(DistRec) / 16) * p.n_dists;
+        for (int i = threadIdx.x; i < n16; i += blockDim.x) s_dists[i] = __ldg(reinterpret_cast<const int4*>(p.dists) + i);
+        for (int i = threadIdx.x; i < p.tab_pool_len; i += blockDim.x) s_tab[i] = __ldg(p.tab_pool + i);
+        dists = smem_base + uint32_t(kLogTabBytes);
+        tab = smem_base + p.smem_tab_off;
+    } else {
+        dists = reinterpret_cast<const char*>(p.dists);
+        tab = reinterpret_cast<const char*>(p.tab_pool);
+    }
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int n_warps = blockDim.x >> 5;
+    const uint32_t ring0 = smem_base + p.smem_ring_off + uint32_t(warp) * uint32_t(kRingStride);
+    const uint32_t bar0 = ring0 + 2u * uint32_t(kChunkBytes);
+    if (lane == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int wpg = DYN ? p.warps_per_group : 1;
+    const int group_in_cta = warp / wpg;
+    const int wsub = warp - group_in_cta * wpg;
+    const int groups_per_cta = n_warps / wpg;
+    const int64_t batch0 = int64_t(blockIdx.x) * groups_per_cta + group_in_cta;
+    if (batch0 * kQuadSamples >= p.n) return;  // whole group (all its warps) out of range
+    const PhiloxKeys& key0 = p.keys;
+
+    // The lane's four sample columns.  ld is a multiple of 64, not necessarily of 128: in the last group the
+    // lanes of the upper half may then lie past the row end.  They shadow the lower half (same columns, same
+    // seeds, hence the same values written twice) and stay out of the statistics.
+    const int64_t seg0 = batch0 * kQuadSamples;
+    const bool half_row = seg0 + 64 >= p.ld;
+    int64_t s0 = seg0 + 4 * lane;
+    const bool shadow = s0 >= p.ld;
+    if (shadow) s0 -= 64;
+    Seeds4 sd;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sd.s[i] = uint32_t(i);
+    if constexpr (MODE != kModeInjected) {
+        if (p.seeds) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                sd.s[i] = s0 + i < p.n ? uint32_t(__ldg(p.seeds + s0 + i)) : (i ? sd.s[i - 1] + 1u : 0u);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sd.s[i] = uint32_t(p.seed0) + uint32_t(s0) + uint32_t(i);
+        }
+    }
+    sd.quad = ((sd.s[0] & 1u) == 0u) && sd.s[1] == sd.s[0] + 1u && sd.s[2] == sd.s[0] + 2u && sd.s[3] == sd.s[0] + 3u;
+    const uint32_t lane_off = uint32_t(s0) * 8u;
+    auto f64_row = [&](const void* base, uint32_t row) -> char* {
+        return const_cast<char*>(reinterpret_cast<const char*>(base)) + (uint64_t(row) * p.ldb8 + lane_off);
+    };
+    auto i32_row = [&](const void* base, uint32_t row) -> char* {
+        return const_cast<char*>(reinterpret_cast<const char*>(base)) + (uint64_t(row) * p.ldb4 + (lane_off >> 1));
+    };
+    const void* const dur_base = MODE == kModeInjected ? static_cast<const void*>(p.inj) : static_cast<const void*>(p.durations);
+    // L2 prefetch of gather rows: lane l covers one 128-byte line of the warp's row segment (8 lines, 4 when
+    // only half of the segment lies inside the row)
+    const uint32_t pf_off = uint32_t(seg0) * 8u + (half_row ? uint32_t(lane & 3) : uint32_t(lane & 7)) * 128u;
+    const uint32_t pf_unit = half_row ? uint32_t(lane >> 2) : uint32_t(lane >> 3);
+    const uint32_t pf_step = half_row ? 8u : 4u;
+
+    // ---- chunk pipeline ----
+    uint32_t buf_sel = 0u, phase = 0u;
+    auto issue = [&](int c, uint32_t b) {
+        if (lane == 0) {
+            mbar_expect_tx(bar0 + b * 8u, uint32_t(kChunkBytes));
+            bulk_copy_g2s(ring0 + b * uint32_t(kChunkBytes), p.chunks + size_t(c) * kChunkUnits, uint32_t(kChunkBytes),
+                          bar0 + b * 8u);
+        }
+    };
+
+    // ---- level cursor (DYN) ----
+    __shared__ int s_cursor[16][2];
+    if constexpr (DYN) {
+        if (wsub == 0 && lane == 0) s_cursor[group_in_cta][0] = 0;
+        group_barrier(1 + group_in_cta, wpg * 32);
+    }
+    int seq = 0;
+    auto grab = [&](int parity) -> int {
+        if constexpr (!DYN) {
+            return seq++;
+        } else {
+            int v = 0;
+            if (lane == 0) v = atomicAdd(&s_cursor[group_in_cta][parity], 1);
+            return __shfl_sync(0xFFFFFFFFu, v, 0);
+        }
+    };
+
+    // ---- the running event of this warp ----
+    bool open = false;
+    uint32_t row = 0u;
+    double lat[4] = {0.0, 0.0, 0.0, 0.0}, ub = 0.0;
+    int cause[4] = {-1, -1, -1, -1};
+    D4 nrs{0.0, 0.0, 0.0, 0.0};
+    uint32_t ev = 0u;
+    double ev_earliest = 0.0;
+    bool valid[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) valid[i] = !shadow && s0 + i < p.n;
+    auto finalize = [&]() {
+        // _core.cpp:348-349
+        double r[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r[i] = ref_min(lat[i], ub);
+        stcg_d4(f64_row(p.realized, row), D4{r[0], r[1], r[2], r[3]});
+        open = false;
+        if constexpr (!DYN) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) lat[i] = r[i];
+        }
+        if constexpr (!kReduced) {
+            __stcs(reinterpret_cast<int4*>(i32_row(p.cause, row)), make_int4(cause[0], cause[1], cause[2], cause[3]));
+        } else {
+            double x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = valid[i] ? r[i] - ev_earliest : 0.0;
+            if (p.sum) {
+                const double t = warp_sum((x[0] + x[1]) + (x[2] + x[3]));
+                if (lane == 0) atomicAdd(p.sum + ev, t);
+            }
+            if (p.sumsq) {
+                const double t = warp_sum((x[0] * x[0] + x[1] * x[1]) + (x[2] * x[2] + x[3] * x[3]));
+                if (lane == 0) atomicAdd(p.sumsq + ev, t);
+            }
+            if (p.late) {
+#pragma unroll
+                for (int t = 0; t < MCDP_MAX_THRESHOLDS; ++t) {
+                    if (t < p.n_thresholds) {
+                        const double th = p.thresholds[t];
+                        int c = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) c += int(valid[i] && x[i] > th);
+                        const int cnt = __reduce_add_sync(0xFFFFFFFFu, c);
+                        if (lane == 0 && cnt) atomicAdd(p.late + size_t(t) * p.E + ev, (unsigned long long)cnt);
+                    }
+                }
+            }
+            if (p.hist) {
+                const int nb = p.n_bins;
+                uint32_t* h = p.hist + size_t(ev) * nb;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int b = min(max(int(floor((x[i] - p.hist_lo) * p.hist_scale)), 0), nb - 1);
+                    if (!valid[i]) b = -1 - lane;  // unique keys: match groups of size 1, skipped below
+                    const unsigned g = __match_any_sync(0xFFFFFFFFu, b);
+                    if (b >= 0 && lane == __ffs(g) - 1) atomicAdd(h + b, uint32_t(__popc(g)));
+                }
+            }
+            if constexpr (MODE == kModeAttr) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int w = valid[i] ? cause[i] : -4 - lane;
+                    const unsigned g = __match_any_sync(0xFFFFFFFFu, w);
+                    if (lane == __ffs(g) - 1) {
+                        if (w >= 0) atomicAdd(p.cause_act + w, (unsigned long long)__popc(g));
+                        else if (w == -1) atomicAdd(p.cause_none + ev, (unsigned long long)__popc(g));
+                    }
+                }
+            }
+        }
+    };
+    auto process = [&](uint32_t buf, int u0, uint32_t remaining) {
+#pragma unroll 1
+        for (int u = u0; u < kChunkUnits; ++u) {
+            const int4 q0 = lds128(buf + uint32_t(u) * 32u);
+            const int4 q1 = lds128(buf + uint32_t(u) * 32u + 16u);
+            const uint32_t meta = uint32_t(q1.x);
+            const uint32_t kind = meta >> 29;
+            // the realized row of the NEXT entry unit is requested before this unit's delays are drawn
+            const D4 rs = nrs;
+            if (DYN || kind < kKindEvent) {
+                if (uint32_t(q1.z) != kNoRow) nrs = ldcg_d4(f64_row(p.realized, uint32_t(q1.z)));
+            }
+            if (kind >= kKindEvent) {
+                if (open) finalize();
+                if (kind == kKindEnd) break;
+                if constexpr (!DYN) {
+                    if (q1.w != 0) nrs = D4{lat[0], lat[1], lat[2], lat[3]};
+                    else if (uint32_t(q1.z) != kNoRow) nrs = ldcg_d4(f64_row(p.realized, uint32_t(q1.z)));
+                }
+                // _core.cpp:333-337
+                row = uint32_t(q0.x);
+                const double earliest = __hiloint2double(q0.w, q0.z);
+                if constexpr (kReduced) {
+                    ev = uint32_t(q0.y);
+                    ev_earliest = earliest;
+                }
+                ub = __dadd_rn(earliest, p.max_delay);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    lat[i] = earliest;
+                    cause[i] = -1;
+                }
+                open = true;
+                continue;
+            }
+            const uint32_t act = uint32_t(q0.y);
+            const double base = __hiloint2double(q0.w, q0.z);
+            double d[4];
+            if constexpr (MODE == kModeInjected) {
+                D4 dd{0.0, 0.0, 0.0, 0.0};
+                if (act != kNoAct) dd = ldcs_d4(f64_row(dur_base, act));
+                d[0] = dd.x;
+                d[1] = dd.y;
+                d[2] = dd.z;
+                d[3] = dd.w;
+            } else {
+                if (kind == kKindNone) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d[i] = base;  // _core.cpp:304-305,325
+                } else {
+                    double e[4];
+                    sample_extra4<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, sd, key0, log_tab, e);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d[i] = __dadd_rn(base, e[i]);  // _core.cpp:328
+                }
+                if constexpr (MODE == kModeFull) {
+                    if (act != kNoAct) stcs_d4(f64_row(dur_base, act), D4{d[0], d[1], d[2], d[3]});
+                }
+            }
+            // _core.cpp:341-346
+            const int src_event = MODE == kModeAttr ? (act == kNoAct ? -3 : int(act)) : q0.x;
+            const double rsv[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double t = ref_min(__dadd_rn(rsv[i], d[i]), ub);
+                if (t >= lat[i]) {
+                    lat[i] = t;
+                    cause[i] = src_event;
+                }
+            }
+        }
+        if (open && remaining == 0u) finalize();
+    };
+
+    // ---- main loop ----
+    const int n_rounds = DYN ? p.n_levels : (p.n_chunks > 0 ? 1 : 0);
+    for (int lvl = 0; lvl < n_rounds; ++lvl) {
+        const int le = DYN ? __ldg(p.chunk_level_begin + lvl + 1) : p.n_chunks;
+        const int par = lvl & 1;
+        if constexpr (DYN) {
+            if (wsub == 0 && lane == 0) s_cursor[group_in_cta][par ^ 1] = le;
+        }
+        int c = grab(par);
+        bool from_cursor = true;
+        if (c < le) issue(c, buf_sel);
+        while (c < le) {
+            const uint32_t buf = ring0 + buf_sel * uint32_t(kChunkBytes);
+            mbar_wait(bar0 + buf_sel * 8u, (phase >> buf_sel) & 1u);
+            phase ^= 1u << buf_sel;
+            buf_sel ^= 1u;
+            const int4 h1 = lds128(buf + 16u);
+            const bool is_cont = (uint32_t(h1.x) >> 29) == kKindEnd;
+            const bool skip = DYN && from_cursor && is_cont;
+            const uint32_t remaining = skip ? 0u : uint32_t(h1.y);
+            from_cursor = remaining == 0u;
+            int cn;
+            if (from_cursor) {
+                cn = grab(par);
+            } else {
+                cn = c + 1;
+                if constexpr (!DYN) ++seq;
+            }
+            if (cn < le) issue(cn, buf_sel);
+            if (!skip) {
+                for (uint32_t uu = pf_unit; uu < uint32_t(kChunkUnits); uu += pf_step) {
+                    const uint32_t ua = buf + uu * 32u;
+                    uint32_t src, meta;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(src) : "r"(ua));
+                    asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(meta) : "r"(ua));
+                    if ((meta >> 29) < kKindEvent)
+                        prefetch_l2(reinterpret_cast<const char*>(p.realized) + (uint64_t(src) * p.ldb8 + pf_off));
+                }
+                process(buf, is_cont ? 1 : 0, remaining);
+            }
+            __syncwarp();
+            c = cn;
+        }
+        if constexpr (DYN) group_barrier(1 + group_in_cta, wpg * 32);
+    }
+
+    if constexpr (MODE == kModeFull) {
+        // activities no precedence entry references still get their sampled duration (_core.cpp:323-329)
+        for (int i = wsub; i < p.n_orphans; i += wpg) {
+            const int4 q0 = __ldg(reinterpret_cast<const int4*>(p.orphans + i));
+            const int4 q1 = __ldg(reinterpret_cast<const int4*>(p.orphans + i) + 1);
+            const uint32_t act = uint32_t(q0.y), meta = uint32_t(q1.x);
+            const double base = __hiloint2double(q0.w, q0.z);
+            double d[4] = {base, base, base, base};
+            if ((meta >> 29) != kKindNone) {
+                double e[4];
+                sample_extra4<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, sd, key0, log_tab, e);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[k] = __dadd_rn(base, e[k]);
+            }
+            stcs_d4(f64_row(dur_base, act), D4{d[0], d[1], d[2], d[3]});
+        }
+    }
+}
+
+}  // namespace mcdp

@@ -1,0 +1,271 @@
+// mcdp_sampling4.cuh -- the generator contract of mcdp_sampling.cuh evaluated for the FOUR adjacent
+// samples a lane owns in the quad sweep (mcdp_quad_sweep.cuh).
+//
+// Nothing about the contract changes: every (seed, activity) pair reads the same Philox blocks and
+// goes through the same transforms as in sample_extra2, so the two kernels return identical bits
+// (tests/test_gpu_parity.py::test_quad_matches_pair).  What changes is the cost structure: the kind
+// dispatch, the distribution-record loads and the Erlang variant switch are taken once per four
+// samples, and four independent dependency chains are in flight per lane.
+//
+// Replaces Dist::sample (reference _core.cpp:72-141) like mcdp_sampling.cuh does.
+#pragma once
+#include "mcdp_sampling.cuh"
+
+namespace mcdp {
+
+// `quad`: the lane's seeds are {4k', 4k'+1, 4k'+2, 4k'+3} up to an even start, i.e. two aligned PAIR
+// blocks (seed >> 1 and (seed >> 1) + 1) serve all four samples.
+struct Seeds4 {
+    uint32_t s[4];
+    bool quad;
+};
+
+// one 64-bit draw per sample from PAIR-style blocks with tag `tag`, draw index j[i]
+__device__ __forceinline__ void draw64x4(const Seeds4& sd, bool same_j, const uint32_t (&j)[4], uint32_t act, uint32_t tag,
+                                         const PhiloxKeys& key0, uint32_t (&lo)[4], uint32_t (&hi)[4]) {
+    if (sd.quad && same_j) {
+        const uint32_t h = sd.s[0] >> 1;
+        const Philox4 r0 = philox4x32_10(h, act, j[0], tag, key0);
+        const Philox4 r1 = philox4x32_10(h + 1u, act, j[2], tag, key0);
+        lo[0] = r0.x;
+        hi[0] = r0.y;
+        lo[1] = r0.z;
+        hi[1] = r0.w;
+        lo[2] = r1.x;
+        hi[2] = r1.y;
+        lo[3] = r1.z;
+        hi[3] = r1.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const Philox4 r = philox4x32_10(sd.s[i] >> 1, act, j[i], tag, key0);
+            const bool odd = sd.s[i] & 1u;
+            lo[i] = odd ? r.z : r.x;
+            hi[i] = odd ? r.w : r.y;
+        }
+    }
+}
+
+// inverse-CDF lookup of four samples in lockstep (emp_value2 widened)
+template <bool SMEM>
+__device__ __forceinline__ void emp_value4(typename Mem<SMEM>::ptr guide_b, typename Mem<SMEM>::ptr cp_b, uint32_t g,
+                                           uint32_t len8, bool scan, const uint32_t (&hi)[4], const double (&u)[4],
+                                           double (&v)[4]) {
+    uint32_t off[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) off[i] = Mem<SMEM>::u32(guide_b + (hi[i] >> (32u - g)) * 4u) * 8u;
+    double c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = Mem<SMEM>::f64(cp_b + off[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) off[i] += c[i] < u[i] ? 8u : 0u;  // cp[len-1] == 1.0 > u: stays in range
+    if (scan) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            while (Mem<SMEM>::f64(cp_b + off[i]) < u[i]) off[i] += 8u;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = Mem<SMEM>::f64(cp_b + off[i] + len8);
+}
+
+// erlang_value for four samples: ONE switch on the warp-uniform variant
+template <bool SMEM>
+__device__ __forceinline__ void erlang_value4(const DistView<SMEM>& d, int variant, const uint32_t (&w0)[4],
+                                              const uint32_t (&w1)[4], const uint32_t (&w2)[4], const uint32_t (&w3)[4],
+                                              uint32_t log_tab, double (&y)[4]) {
+    double e[4];
+    switch (variant) {
+        case 1:
+#pragma unroll
+            for (int i = 0; i < 4; ++i) e[i] = half_term(w0[i], w1[i], log_tab);
+            break;
+        case 2:
+#pragma unroll
+            for (int i = 0; i < 4; ++i) e[i] = -log_pos(uniform32(w0[i]), log_tab);
+            break;
+        case 3:
+#pragma unroll
+            for (int i = 0; i < 4; ++i) e[i] = half_term(w1[i], w2[i], log_tab) - log_pos(uniform32(w0[i]), log_tab);
+            break;
+        case 4:
+#pragma unroll
+            for (int i = 0; i < 4; ++i) e[i] = -log_pos(uniform32(w0[i]) * uniform32(w1[i]), log_tab);
+            break;
+        case 5:
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                e[i] = half_term(w2[i], w3[i], log_tab) - log_pos(uniform32(w0[i]) * uniform32(w1[i]), log_tab);
+            break;
+        case 6:
+#pragma unroll
+            for (int i = 0; i < 4; ++i) e[i] = -log_pos(uniform32(w0[i]) * uniform32(w1[i]) * uniform32(w2[i]), log_tab);
+            break;
+        default:
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                e[i] = -log_pos((uniform32(w0[i]) * uniform32(w1[i])) * (uniform32(w2[i]) * uniform32(w3[i])), log_tab);
+            break;
+    }
+    const double scale = d.p(1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = scale * e[i];
+}
+
+// draw j[i] of the four samples (erlang_draw2 widened; same blocks and word order)
+template <bool SMEM>
+__device__ __forceinline__ void erlang_draw4(const DistView<SMEM>& d, int variant, const Seeds4& sd, bool same_j,
+                                             const uint32_t (&j)[4], uint32_t act, const PhiloxKeys& key0, uint32_t log_tab,
+                                             double (&y)[4]) {
+    uint32_t w0[4], w1[4], w2[4] = {0u, 0u, 0u, 0u}, w3[4] = {0u, 0u, 0u, 0u};
+    if (variant <= 2 || variant == 4) {  // <= 64 bits per sample: PAIR-style blocks
+        draw64x4(sd, same_j, j, act, kTagErlang, key0, w0, w1);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const Philox4 r = philox4x32_10(sd.s[i], act, j[i], kTagErlang, key0);
+            w0[i] = r.x;
+            w1[i] = r.y;
+            w2[i] = r.z;
+            w3[i] = r.w;
+        }
+    }
+    erlang_value4<SMEM>(d, variant, w0, w1, w2, w3, log_tab, y);
+}
+
+template <bool SMEM>
+__device__ __forceinline__ void erlang_variate4(const DistView<SMEM>& d, const Seeds4& sd, uint32_t act,
+                                                const PhiloxKeys& key0, uint32_t log_tab, double (&x)[4]) {
+    const int variant = 2 * d.pad0() + d.pad1();
+    const double mx = d.p(2);
+    uint32_t j[4] = {0u, 0u, 0u, 0u};
+    erlang_draw4<SMEM>(d, variant, sd, true, j, act, key0, log_tab, x);
+    // truncation (_core.cpp:98-104): draws 1, 2, ... until x <= max_scale; rare, so off the straight path
+    bool need[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) need[i] = x[i] > mx;
+    if (__any_sync(0xFFFFFFFFu, need[0] || need[1] || need[2] || need[3])) {
+        do {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) j[i] += need[i] ? 1u : 0u;
+            double y[4];
+            erlang_draw4<SMEM>(d, variant, sd, j[0] == j[1] && j[2] == j[3], j, act, key0, log_tab, y);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (need[i]) {
+                    x[i] = y[i];
+                    need[i] = y[i] > mx && j[i] + 1u < kGammaMaxAttempts;
+                }
+            }
+        } while (__any_sync(0xFFFFFFFFu, need[0] || need[1] || need[2] || need[3]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = x[i] > mx ? mx : x[i];  // only after the attempt cap
+    }
+}
+
+// Marsaglia-Tsang for four samples: first attempts straight-line, then ONE warp-wide retry loop in which
+// every lane retries its first pending sample (gamma_variate2 widened; same SOLO blocks per attempt).
+template <bool SMEM>
+__device__ __forceinline__ void gamma_variate4(const DistView<SMEM>& d, const Seeds4& sd, uint32_t act,
+                                               const PhiloxKeys& key0, double (&x)[4]) {
+    bool need[4];
+    {
+        const Philox4 wa = philox4x32_10(sd.s[0], act, 0u, kTagSolo, key0);
+        const Philox4 wb = philox4x32_10(sd.s[1], act, 0u, kTagSolo, key0);
+        gamma_eval2<SMEM>(d, wa, wb, x[0], x[1], need[0], need[1]);
+    }
+    {
+        const Philox4 wc = philox4x32_10(sd.s[2], act, 0u, kTagSolo, key0);
+        const Philox4 wd = philox4x32_10(sd.s[3], act, 0u, kTagSolo, key0);
+        gamma_eval2<SMEM>(d, wc, wd, x[2], x[3], need[2], need[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) need[i] = !need[i];
+    uint32_t t[4] = {1u, 1u, 1u, 1u};
+    while (__any_sync(0xFFFFFFFFu, need[0] || need[1] || need[2] || need[3])) {
+        const int idx = need[0] ? 0 : (need[1] ? 1 : (need[2] ? 2 : 3));
+        const uint32_t seed = idx == 0 ? sd.s[0] : (idx == 1 ? sd.s[1] : (idx == 2 ? sd.s[2] : sd.s[3]));
+        const uint32_t tt = idx == 0 ? t[0] : (idx == 1 ? t[1] : (idx == 2 ? t[2] : t[3]));
+        double xx;
+        const bool ok = gamma_eval<SMEM>(d, philox4x32_10(seed, act, tt, kTagSolo, key0), xx);
+        const bool give_up = tt + 1u >= kGammaMaxAttempts;  // the reference would spin forever: clamp
+        if (give_up) xx = fmin(xx, d.p(2));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (idx == i && need[i]) {
+                ++t[i];
+                if (ok || give_up) {
+                    x[i] = xx;
+                    need[i] = false;
+                }
+            }
+        }
+    }
+}
+
+// Extra delays of one activity for the four samples of a lane (sample_extra2 widened).
+template <bool SMEM>
+__device__ __forceinline__ void sample_extra4(uint32_t meta, uint32_t tab_off, typename Mem<SMEM>::ptr dists, uint32_t dist,
+                                              typename Mem<SMEM>::ptr tab, double base, uint32_t act, const Seeds4& sd,
+                                              const PhiloxKeys& key0, uint32_t log_tab, double (&e)[4]) {
+    const uint32_t kind = meta >> 29;
+    if (kind == MCDP_DIST_CONSTANT) {
+        const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
+        const double c = __dmul_rn(base, d.p(0));  // _core.cpp:75
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = c;
+        return;
+    }
+    if (kind == MCDP_DIST_GAMMA) {
+        const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
+        double x[4];
+        if (d.flags() & 8)
+            erlang_variate4<SMEM>(d, sd, act, key0, log_tab, x);
+        else
+            gamma_variate4<SMEM>(d, sd, act, key0, x);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = __dmul_rn(x[i], base);
+        return;
+    }
+    // one 64-bit draw per sample
+    uint32_t lo[4], hi[4];
+    const uint32_t j0[4] = {0u, 0u, 0u, 0u};
+    draw64x4(sd, true, j0, act, kTagPair, key0, lo, hi);
+    double u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = uniform52(lo[i], hi[i]);
+    if (kind == MCDP_DIST_EXPONENTIAL) {
+        // inverse CDF of the exponential truncated to [0, max_scale] (see sample_extra2; _core.cpp:83-89)
+        const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
+        const double lam = d.p(0), mx = d.p(1), F = d.p(2);
+        double x[4];
+        if (d.flags() & 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = lam * neg_log1m(u[i] * F, true, log_tab);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = lam * neg_log1m(u[i] * F, false, log_tab);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            x[i] = x[i] > mx ? mx : x[i];
+            e[i] = __dmul_rn(x[i], base);
+        }
+        return;
+    }
+    // empirical tables (pool block layout: see sample_extra2)
+    const uint32_t g = (meta >> 24) & 31u, len8 = (meta & 0x7FFFFFu) * 8u;
+    const bool scan = meta & 0x800000u;
+    const typename Mem<SMEM>::ptr guide_b = tab + tab_off;
+    const typename Mem<SMEM>::ptr cp_b = tab + dist;
+    double v[4];
+    emp_value4<SMEM>(guide_b, cp_b, g, len8, scan, hi, u, v);
+    if (kind == MCDP_DIST_EMP_ABS) {  // _core.cpp:125
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = v[i];
+    } else {  // _core.cpp:140
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[i] = __dmul_rn(v[i], base);
+    }
+}
+
+}  // namespace mcdp

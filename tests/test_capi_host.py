@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = capi.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mcdp_abi_version() == 2
+    assert lib.mcdp_abi_version() == 3
 
 
 def test_no_cpu_execution_path():
@@ -137,3 +137,35 @@ def test_benchmark_configs_compile():
     dag, d = synth.c5_deep_chain()
     plan = capi.Plan(dag, d, device=capi.DEVICE_NONE)
     assert plan.n_levels == 50_001 + 1 - 1 or plan.n_levels >= 50_000
+
+
+def test_launch_shape_of_both_kernels():
+    """mcdp_plan_launch_shape on a host-only plan (148 SMs assumed): the pair kernel covers 64 samples per group at
+    32 resident warps per SM, the quad kernel 128 samples per group at 16; the bench workload's C3 batch is one full
+    wave for either."""
+    dag, d = synth.c2_layered()
+    plan = capi.Plan(dag, d, device=capi.DEVICE_NONE)
+    n = 18944  # 296 pair groups = 148 quad groups
+    plan.set_option(capi.OPT_SAMPLES_PER_LANE, 2)
+    plan.set_option(capi.OPT_WARPS_PER_GROUP, 16)
+    s2 = plan.launch_shape(n)
+    assert (s2["samples_per_lane"], s2["warps_per_group"], s2["threads"], s2["grid"]) == (2, 16, 512, 296)
+    plan.set_option(capi.OPT_SAMPLES_PER_LANE, 4)
+    s4 = plan.launch_shape(n)
+    assert (s4["samples_per_lane"], s4["warps_per_group"], s4["threads"], s4["grid"]) == (4, 16, 512, 148)
+    assert s4["smem_bytes"] == s2["smem_bytes"]  # same tables + one chunk ring per warp
+    # ragged counts round up to whole groups
+    plan.set_option(capi.OPT_WARPS_PER_GROUP, 1)
+    plan.set_option(capi.OPT_GROUPS_PER_CTA, 1)
+    assert plan.launch_shape(129)["grid"] == 2 and plan.launch_shape(128)["grid"] == 1 and plan.launch_shape(1)["grid"] == 1
+    plan.set_option(capi.OPT_SAMPLES_PER_LANE, 2)
+    assert plan.launch_shape(129)["grid"] == 3
+    # multi-batch reduced launches (more 64-sample batches than warp slots) stay on the pair path
+    plan.set_option(capi.OPT_SAMPLES_PER_LANE, 4)
+    plan.set_option(capi.OPT_WARPS_PER_GROUP, 0)
+    plan.set_option(capi.OPT_GROUPS_PER_CTA, 0)
+    big = plan.launch_shape(1 << 20, reduced=True, n_bins=64)
+    assert big["batches"] > 1 and big["samples_per_lane"] == 2
+    assert plan.launch_shape(1 << 15, reduced=True, n_bins=64)["samples_per_lane"] == 4
+    with pytest.raises(RuntimeError, match="samples per lane"):
+        plan.set_option(capi.OPT_SAMPLES_PER_LANE, 3)

@@ -1,0 +1,181 @@
+"""GPU parity tests of the quad sweep kernel (four samples per lane, ``MCDP_OPT_SAMPLES_PER_LANE = 4``,
+mc_dagprop_b200/csrc/mcdp_quad_sweep.cuh), called through the C ABI.
+
+The quad kernel must return exactly what the pair kernel returns (same generator contract, same recurrence):
+  * duration injection: realized bit-exact in fp64, cause_event exact against the CPU oracle;
+  * fused sampling: durations / realized / cause bit-identical to the pair kernel for paired, unpaired,
+    arbitrary and extreme seeds, for every distribution kind (Erlang-shape and Marsaglia-Tsang gamma included);
+  * reduced statistics and delay-cause attribution: integer accumulators exact, fp64 sums to summation order;
+  * ragged sample counts, row lengths that are a multiple of 64 but not of 128 (shadow lanes), buffers that
+    are only 16-byte aligned (falls back to the pair kernel).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from mc_dagprop_b200 import capi, synth
+from mc_dagprop_b200.flat import FlatDists
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+def _plan(dag, dists, spl, wpg=0, gpc=0, chunk=0):
+    plan = capi.Plan(dag, dists, device=0)
+    plan.set_option(capi.OPT_SAMPLES_PER_LANE, spl)
+    if wpg:
+        plan.set_option(capi.OPT_WARPS_PER_GROUP, wpg)
+    if gpc:
+        plan.set_option(capi.OPT_GROUPS_PER_CTA, gpc)
+    if chunk:
+        plan.set_option(capi.OPT_HOST_CHUNK, chunk)
+    return plan
+
+
+def _all_kinds_dists() -> FlatDists:
+    """mixed_small_dists plus every Erlang-shape gamma variant and a truncating max_scale."""
+    d = synth.mixed_small_dists()
+    for t, shape in enumerate((0.5, 1.0, 1.5, 2.0, 3.0, 3.5, 4.0), start=7):
+        d.add_gamma(t, shape, 0.3, 0.8 if t % 2 else 5.0)
+    return d
+
+
+@pytest.mark.parametrize("n_events,seed", [(2, 0), (17, 1), (200, 2), (1500, 3)])
+@pytest.mark.parametrize("wpg", [1, 3, 8, 16])
+def test_quad_injected_bit_exact_random_dags(n_events, seed, wpg):
+    dag = synth.random_dag(n_events, seed)
+    dists = synth.mixed_small_dists()
+    osim = oracle.OracleSim(dag, dists)
+    _, dur, _ = osim.run_many(np.arange(-7, 150, dtype=np.int32))  # 157 samples: ld = 192, shadow lanes in group 1
+    r_o, c_o = osim.run_injected(dur)
+    r_d, c_d = _plan(dag, dists, 4, wpg=wpg).run_injected_host(dur)
+    assert np.array_equal(_bits(r_o), _bits(r_d))
+    assert np.array_equal(c_o, c_d)
+
+
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 127, 128, 129, 200, 999])
+def test_quad_injected_ragged_counts(n):
+    dag = synth.random_dag(150, 9, max_delay=25.0)
+    dists = synth.mixed_small_dists()
+    osim = oracle.OracleSim(dag, dists)
+    _, dur, _ = osim.run_many(np.arange(n, dtype=np.int32))
+    r_o, c_o = osim.run_injected(dur)
+    for chunk in (0, 192):
+        r_d, c_d = _plan(dag, dists, 4, chunk=chunk).run_injected_host(dur)
+        assert np.array_equal(_bits(r_o), _bits(r_d))
+        assert np.array_equal(c_o, c_d)
+
+
+@pytest.mark.parametrize("wpg", [0, 1, 4, 16])
+def test_quad_matches_pair(wpg):
+    """Fused sampling + sweep: bit-identical outputs from both kernels, self-consistent through the oracle."""
+    dag = synth.random_dag(400, 20, n_types=14)
+    dists = _all_kinds_dists()
+    rng = np.random.default_rng(wpg)
+    # aligned quads, odd start (no pairs), pairs that are not quads, arbitrary, extremes
+    seeds = np.concatenate([np.arange(0, 260), np.arange(1001, 1100), np.arange(2, 80), rng.integers(-2**31, 2**31 - 1, size=100),
+                            [-1, 2**31 - 1, -2**31]]).astype(np.int32)
+    r2, d2, c2 = _plan(dag, dists, 2, wpg=wpg).run_many_host(seeds)
+    r4, d4, c4 = _plan(dag, dists, 4, wpg=wpg).run_many_host(seeds)
+    assert np.array_equal(_bits(d2), _bits(d4))
+    assert np.array_equal(_bits(r2), _bits(r4))
+    assert np.array_equal(c2, c4)
+    osim = oracle.OracleSim(dag, dists)
+    ro, co = osim.run_injected(d4)
+    assert np.array_equal(_bits(ro), _bits(r4)) and np.array_equal(co, c4)
+    # a sample is a pure function of its seed: permuting the seeds changes nothing
+    perm = rng.permutation(seeds.size)
+    r5, d5, c5 = _plan(dag, dists, 4, wpg=wpg, chunk=256).run_many_host(seeds[perm])
+    assert np.array_equal(_bits(d5), _bits(d4[perm])) and np.array_equal(_bits(r5), _bits(r4[perm]))
+    assert np.array_equal(c5, c4[perm])
+
+
+def test_quad_matches_generator_contract():
+    dag = synth.random_dag(300, 11)
+    dists = synth.mixed_small_dists()
+    osim = oracle.OracleSim(dag, dists)
+    seeds = np.arange(-3, 253, dtype=np.int32)
+    _, d, _ = _plan(dag, dists, 4).run_many_host(seeds)
+    _, d_spec, _ = osim.run_many_spec(seeds)
+    kinds = {t: k for t, k in zip(dists.dist_type.tolist(), dists.kind.tolist())}
+    act_kind = np.full(osim.A, -1)
+    for i, t in zip(dag.act_idx.tolist(), dag.act_type.tolist()):
+        act_kind[i] = kinds.get(t, -1)
+    exact = np.isin(act_kind, [-1, 0, 3, 4])
+    assert np.array_equal(_bits(d[:, exact]), _bits(d_spec[:, exact]))
+    expo = act_kind == 1
+    np.testing.assert_allclose(d[:, expo], d_spec[:, expo], rtol=1e-9, atol=1e-12)
+    gam = act_kind == 2
+    assert np.isclose(d[:, gam], d_spec[:, gam], rtol=5e-5, atol=1e-9).mean() > 0.9995
+
+
+@pytest.mark.parametrize("wpg", [1, 4])
+def test_quad_reduced_and_attribution_match_pair(wpg):
+    dag = synth.random_dag(500, 41, max_delay=40.0)
+    dists = synth.mixed_small_dists()
+    seeds = np.arange(3, 3 + 2001, dtype=np.int32)
+    th = (1.0, 5.0, 20.0)
+    kw = dict(thresholds=th, n_bins=16, hist_range=(0.0, 40.0))
+    p2, p4 = _plan(dag, dists, 2, wpg=wpg), _plan(dag, dists, 4, wpg=wpg)
+    s2, s4 = p2.run_reduced_host(seeds, **kw), p4.run_reduced_host(seeds, **kw)
+    assert np.array_equal(s2.hist, s4.hist) and np.array_equal(s2.late, s4.late)
+    assert int(s4.hist.sum()) == seeds.size * p4.E
+    np.testing.assert_allclose(s4.sum, s2.sum, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(s4.sumsq, s2.sumsq, rtol=1e-12, atol=1e-9)
+    # against the full outputs
+    r, _, c = p4.run_many_host(seeds)
+    delay = r - dag.earliest[None, :]
+    for i, t in enumerate(th):
+        assert np.array_equal(s4.late[i], (delay > t).sum(0).astype(np.uint64))
+    (a2, act2, none2), (a4, act4, none4) = p2.run_attribution_host(seeds, **kw), p4.run_attribution_host(seeds, **kw)
+    assert np.array_equal(act2, act4) and np.array_equal(none2, none4) and np.array_equal(a2.hist, a4.hist)
+    assert np.array_equal(none4, (c == -1).sum(0).astype(np.uint64))
+
+
+@pytest.mark.parametrize("seed0", [0, 4096, 7, -6, 2])
+@pytest.mark.parametrize("ld,offset", [(320, 0), (384, 0), (320, 2), (384, 2)])
+def test_quad_device_call_layouts(seed0, ld, offset):
+    """Device-buffer calls: row lengths 64 * odd (shadow lanes) and 128-multiples; buffers offset by 16 bytes are not
+    32-byte aligned, so the call takes the pair kernel -- the result must not depend on any of it."""
+    import torch
+
+    dag, dists = synth.random_dag(400, 21), synth.mixed_small_dists()
+    plan = _plan(dag, dists, 4)
+    n = 300
+    E, A = plan.E, plan.A
+    dev = torch.device("cuda:0")
+    rb = torch.zeros(E * ld + 4, dtype=torch.float64, device=dev)
+    db = torch.zeros(A * ld + 4, dtype=torch.float64, device=dev)
+    cb = torch.zeros(E * ld + 8, dtype=torch.int32, device=dev)
+    r = rb[offset:offset + E * ld].view(E, ld)
+    d = db[offset:offset + A * ld].view(A, ld)
+    c = cb[2 * offset:2 * offset + E * ld].view(E, ld)
+    plan.run_full_device(n, r, d, c, ld, seed0=seed0)
+    torch.cuda.synchronize()
+    seeds = np.arange(seed0, seed0 + n, dtype=np.int32)
+    r_h, d_h, c_h = _plan(dag, dists, 2).run_many_host(seeds)
+    assert np.array_equal(_bits(r[:, :n].T.cpu().numpy()), _bits(r_h))
+    assert np.array_equal(_bits(d[:, :n].T.cpu().numpy()), _bits(d_h))
+    assert np.array_equal(c[:, :n].T.cpu().numpy(), c_h)
+    # nothing outside the row range was touched
+    assert float(rb[:offset].abs().sum()) == 0.0 and float(rb[offset + E * ld:].abs().sum()) == 0.0
+    assert float(db[:offset].abs().sum()) == 0.0 and float(db[offset + A * ld:].abs().sum()) == 0.0
+    # injected through device buffers
+    r2 = torch.zeros_like(r)
+    c2 = torch.zeros_like(c)
+    plan.run_injected_device(n, d, r2, c2, ld)
+    torch.cuda.synchronize()
+    assert np.array_equal(_bits(r2[:, :n].T.cpu().numpy()), _bits(r_h))
+    assert np.array_equal(c2[:, :n].T.cpu().numpy(), c_h)
+
+
+def test_quad_full_size_c3_slice_matches_pair():
+    """The bench workload's DAG (100k events / 399k activities) on one 128-sample group per kernel."""
+    dag, dists = synth.c3_network()
+    seeds = np.arange(1000, 1000 + 192, dtype=np.int32)
+    r2, d2, c2 = _plan(dag, dists, 2).run_many_host(seeds)
+    r4, d4, c4 = _plan(dag, dists, 4).run_many_host(seeds)
+    assert np.array_equal(_bits(d2), _bits(d4)) and np.array_equal(_bits(r2), _bits(r4)) and np.array_equal(c2, c4)
