@@ -199,12 +199,10 @@ struct LaunchShape {
     int n_bins;
 };
 
-// Which kernel "auto" means.  Measured on B200 (profiles/r01_quad_ab.txt): see DESIGN.md section 5.
-constexpr int kAutoSamplesPerLane = MCDP_AUTO_SPL;
-
-// How many warps split a level, how many sample groups share a CTA, which kernel runs them.
-LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false, int n_bins = 0, bool single_batch = false,
-                         int force_spl = 0) {
+// How many warps split a level and how many sample groups share a CTA for the kernel with `spl` samples per lane;
+// `eff_out` = share of the SMs' warp slots the launch keeps busy over whole waves.
+LaunchShape choose_shape_spl(const mcdp_plan* plan, int64_t n, bool reduced, int n_bins, bool single_batch, int spl,
+                             double* eff_out) {
     const HostPlan& h = plan->host;
     LaunchShape s{};
     s.reduced = reduced;
@@ -220,7 +218,6 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false,
         n_groups = (n_groups + batches - 1) / batches;
     }
     // the quad kernel covers everything but the multi-batch reduced launches (mcdp_sweep.cuh)
-    int spl = force_spl ? force_spl : (plan->samples_per_lane ? plan->samples_per_lane : kAutoSamplesPerLane);
     if (batches > 1) spl = 2;
     s.spl = spl;
     const int sm_warps = spl == 4 ? 16 : 32;  // resident warps per SM: 128 vs 64 registers per thread
@@ -230,11 +227,12 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false,
     int gpc = plan->groups_per_cta;
     if (wpg <= 0) {
         // Candidates: power-of-two warps per group, bounded by what the levels can feed (>= 4 events
-        // per warp per level on average).  Pick the shape that keeps the most warp slots busy over
-        // whole waves (32 warps per SM); ties go to more warps per group: fewer resident samples per
+        // per warp per level on average; 8 in the quad kernel, whose single CTA per SM has no second
+        // group to run while one waits at a level barrier).  Pick the shape that keeps the most warp
+        // slots busy over whole waves; ties go to more warps per group: fewer resident samples per
         // SM shorten the reuse distance of realized rows in L2.
         const int64_t avg_width = h.n_levels > 0 ? h.E / h.n_levels : 1;
-        const int64_t by_width = std::max<int64_t>(1, avg_width / 4);
+        const int64_t by_width = std::max<int64_t>(1, avg_width / (spl == 4 ? 8 : 4));
         double best = -1.0;
         for (int cand = 1; cand <= kMaxWarps && cand <= by_width; cand *= 2) {
             const int g = gpc > 0 ? std::min(gpc, kMaxWarps / cand) : std::max(1, 8 / cand);
@@ -258,12 +256,35 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false,
     s.batches = batches;
     s.threads = 32 * wpg * gpc;
     s.grid = unsigned((n_groups + gpc - 1) / gpc);
+    if (eff_out) {
+        const int64_t per_sm = std::max(1, sm_warps / (wpg * gpc));
+        const int64_t slots = int64_t(plan->sm_count) * per_sm;
+        const int64_t waves = std::max<int64_t>(1, (int64_t(s.grid) + slots - 1) / slots);
+        *eff_out = double(n_groups * wpg) / double(waves * plan->sm_count * sm_warps);
+    }
     const size_t need = sizeof(DistRec) * h.dists.size() + sizeof(double) * h.tab_pool.size();
     // keep several CTAs per SM resident: stage only when the tables are a modest share of shared memory
     s.smem_tables = need > 0 && need <= std::min<size_t>(plan->smem_optin, 64 * 1024);
     s.smem = size_t(kLogTabBytes) + (s.smem_tables ? need : 0);  // the log table of mcdp_math.cuh is always staged
     if (reduced && n_bins > 0 && batches > 1) s.smem = ((s.smem + 15) & ~size_t(15)) + size_t(wpg * gpc) * size_t(n_bins) * 4;
     return s;
+}
+
+// Which kernel "auto" means.  On B200 the quad kernel is 10-15 % faster on every named workload once its launch
+// fills the machine (profiles/r01_quad_ab.txt), but its groups are twice as large: a launch too small to give every
+// SM a quad group runs faster as pair groups spread over twice as many SMs (C3 at 9 472 samples: 21.8 vs 28.4 ms).
+constexpr int kAutoSamplesPerLane = MCDP_AUTO_SPL;
+constexpr double kQuadMinFill = 0.8;
+
+LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false, int n_bins = 0, bool single_batch = false,
+                         int force_spl = 0) {
+    const int want = force_spl ? force_spl : plan->samples_per_lane;
+    if (want) return choose_shape_spl(plan, n, reduced, n_bins, single_batch, want, nullptr);
+    double e2 = 0.0, e4 = 0.0;
+    const LaunchShape s2 = choose_shape_spl(plan, n, reduced, n_bins, single_batch, 2, &e2);
+    if (kAutoSamplesPerLane != 4) return s2;
+    const LaunchShape s4 = choose_shape_spl(plan, n, reduced, n_bins, single_batch, 4, &e4);
+    return (s4.spl == 4 && (e4 >= kQuadMinFill || e4 > e2 + 0.1)) ? s4 : s2;
 }
 
 template <typename K>

@@ -42,7 +42,7 @@ constexpr int kQuadSamples = 128;  // samples per group
 
 // what MCDP_OPT_SAMPLES_PER_LANE = 0 (auto) selects
 #ifndef MCDP_AUTO_SPL
-#define MCDP_AUTO_SPL 2
+#define MCDP_AUTO_SPL 4
 #endif
 
 template <int MODE, bool SMEM, bool DYN>

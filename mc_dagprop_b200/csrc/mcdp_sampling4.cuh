@@ -13,8 +13,8 @@
 
 namespace mcdp {
 
-// `quad`: the lane's seeds are {4k', 4k'+1, 4k'+2, 4k'+3} up to an even start, i.e. two aligned PAIR
-// blocks (seed >> 1 and (seed >> 1) + 1) serve all four samples.
+// `quad`: the lane's seeds are s, s+1, s+2, s+3 with s even, i.e. two aligned PAIR blocks (s >> 1 and
+// (s + 2) >> 1) serve all four samples.
 struct Seeds4 {
     uint32_t s[4];
     bool quad;
@@ -24,9 +24,9 @@ struct Seeds4 {
 __device__ __forceinline__ void draw64x4(const Seeds4& sd, bool same_j, const uint32_t (&j)[4], uint32_t act, uint32_t tag,
                                          const PhiloxKeys& key0, uint32_t (&lo)[4], uint32_t (&hi)[4]) {
     if (sd.quad && same_j) {
-        const uint32_t h = sd.s[0] >> 1;
-        const Philox4 r0 = philox4x32_10(h, act, j[0], tag, key0);
-        const Philox4 r1 = philox4x32_10(h + 1u, act, j[2], tag, key0);
+        // (s[2] >> 1, not (s[0] >> 1) + 1: the seeds wrap from 0xFFFFFFFF to 0 inside a quad that starts at -2)
+        const Philox4 r0 = philox4x32_10(sd.s[0] >> 1, act, j[0], tag, key0);
+        const Philox4 r1 = philox4x32_10(sd.s[2] >> 1, act, j[2], tag, key0);
         lo[0] = r0.x;
         hi[0] = r0.y;
         lo[1] = r0.z;
