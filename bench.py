@@ -207,8 +207,13 @@ def run_b200(args):
         plan.set_option(capi.OPT_WARPS_PER_GROUP, args.wpg)
     if args.gpc:
         plan.set_option(capi.OPT_GROUPS_PER_CTA, args.gpc)
+    if args.spl:
+        plan.set_option(capi.OPT_SAMPLES_PER_LANE, args.spl)
     E, A = plan.E, plan.A
     n = args.samples or WORKLOADS[wl][1]
+    shape = plan.launch_shape(n, reduced, 64 if reduced else 0)
+    kernel_name = "mcdp::quad_sweep_kernel" if shape["samples_per_lane"] == 4 else (
+        "mcdp::sweep_kernel" if shape["batches"] > 1 else "mcdp::chunk_sweep_kernel")
     ld = n
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
@@ -266,7 +271,8 @@ def run_b200(args):
     achieved = n * A * bpe / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "bytes_per_edge_sample": bpe,
-                "kernel": "mcdp::chunk_sweep_kernel", "avg_launch_ms": avg_launch_s * 1e3}
+                "kernel": kernel_name, "avg_launch_ms": avg_launch_s * 1e3,
+                "launch": {k: shape[k] for k in ("samples_per_lane", "warps_per_group", "groups_per_cta", "threads", "grid")}}
     prof = os.path.join(ROOT, "profiles", f"traffic_{wl}.json")
     if os.path.exists(prof):
         try:
@@ -372,6 +378,7 @@ def main():
     ap.add_argument("--reduced", action="store_true", help="force the reduced statistics mode")
     ap.add_argument("--wpg", type=int, default=0)
     ap.add_argument("--gpc", type=int, default=0)
+    ap.add_argument("--spl", type=int, default=0, choices=[0, 2, 4], help="samples per lane: 2 pair kernel, 4 quad kernel, 0 auto")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()

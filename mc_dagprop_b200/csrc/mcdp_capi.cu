@@ -220,11 +220,12 @@ LaunchShape choose_shape_spl(const mcdp_plan* plan, int64_t n, bool reduced, int
     // the quad kernel covers everything but the multi-batch reduced launches (mcdp_sweep.cuh)
     if (batches > 1) spl = 2;
     s.spl = spl;
-    const int sm_warps = spl == 4 ? 16 : 32;  // resident warps per SM: 128 vs 64 registers per thread
+    const int sm_warps = spl == 4 ? MCDP_QUAD_MAX_THREADS / 32 : 32;  // resident warps per SM: 96 vs 64 registers per thread
     if (spl == 4) n_groups = (n + kQuadSamples - 1) / kQuadSamples;
     int wpg = plan->warps_per_group;
-    constexpr int kMaxWarps = MCDP_MAX_THREADS / 32;
+    const int kMaxWarps = (spl == 4 ? MCDP_QUAD_MAX_THREADS : MCDP_MAX_THREADS) / 32;
     int gpc = plan->groups_per_cta;
+    const int gpc_warps = spl == 4 ? 10 : 8;  // default CTA: about this many warps (two CTAs per SM / four)
     if (wpg <= 0) {
         // Candidates: power-of-two warps per group, bounded by what the levels can feed (>= 4 events
         // per warp per level on average; 8 in the quad kernel, whose single CTA per SM has no second
@@ -234,8 +235,14 @@ LaunchShape choose_shape_spl(const mcdp_plan* plan, int64_t n, bool reduced, int
         const int64_t avg_width = h.n_levels > 0 ? h.E / h.n_levels : 1;
         const int64_t by_width = std::max<int64_t>(1, avg_width / (spl == 4 ? 8 : 4));
         double best = -1.0;
-        for (int cand = 1; cand <= kMaxWarps && cand <= by_width; cand *= 2) {
-            const int g = gpc > 0 ? std::min(gpc, kMaxWarps / cand) : std::max(1, 8 / cand);
+        // pair kernel: powers of two (32 warp slots per SM); quad kernel: also the divisors of its 20 slots
+        static const int kCandPair[] = {1, 2, 4, 8, 16}, kCandQuad[] = {1, 2, 4, 5, 8, 10, 16, 20};
+        const int* cands = spl == 4 ? kCandQuad : kCandPair;
+        const int n_cands = spl == 4 ? 8 : 5;
+        for (int ci = 0; ci < n_cands; ++ci) {
+            const int cand = cands[ci];
+            if (cand > kMaxWarps || cand > by_width) break;
+            const int g = gpc > 0 ? std::min(gpc, kMaxWarps / cand) : std::max(1, gpc_warps / cand);
             const int64_t ctas = (n_groups + g - 1) / g;
             const int64_t per_sm = std::max(1, sm_warps / (cand * g));
             const int64_t slots = int64_t(plan->sm_count) * per_sm;
@@ -249,7 +256,7 @@ LaunchShape choose_shape_spl(const mcdp_plan* plan, int64_t n, bool reduced, int
         wpg = std::max(wpg, 1);
     }
     wpg = std::max(1, std::min(wpg, kMaxWarps));
-    if (gpc <= 0) gpc = std::max(1, 8 / wpg);
+    if (gpc <= 0) gpc = std::max(1, gpc_warps / wpg);
     gpc = std::max(1, std::min({gpc, 15, kMaxWarps / wpg}));
     s.wpg = wpg;
     s.gpc = gpc;
@@ -595,7 +602,8 @@ int32_t mcdp_plan_set_option(mcdp_plan* plan, int32_t option, int64_t value) {
     switch (option) {
         case MCDP_OPT_STREAM_KEY: plan->stream_key = uint32_t(value); break;
         case MCDP_OPT_WARPS_PER_GROUP:
-            if (value < 0 || value > MCDP_MAX_THREADS / 32) return fail(MCDP_ERR_ARG, "warps per group must be 0..16");
+            if (value < 0 || value > std::max(MCDP_MAX_THREADS, MCDP_QUAD_MAX_THREADS) / 32)
+                return fail(MCDP_ERR_ARG, "warps per group out of range (0 = auto, at most 16 for 512-thread CTAs)");
             plan->warps_per_group = int(value);
             break;
         case MCDP_OPT_GROUPS_PER_CTA:

@@ -8,8 +8,8 @@
 //   * the warp-uniform work of a stream unit -- record words, kind dispatch, distribution-record
 //     loads, row address arithmetic, loop control -- is paid once per 128 edge-samples instead of
 //     once per 64, and four independent dependency chains per lane are in flight;
-//   * one CTA of up to 16 warps per SM at 128 registers: the register file no longer shapes the
-//     loop body (the pair kernel sits at the 64-register spill edge).
+//   * up to 20 warps per SM at 96 registers (one CTA of 20 warps, or two of 10): the register file no
+//     longer shapes the loop body (the pair kernel sits at the 64-register spill edge).
 // Results are bit-identical to the pair kernel (same generator contract, same recurrence).
 #pragma once
 #include "mcdp_chunk_sweep.cuh"
@@ -40,13 +40,20 @@ __device__ __forceinline__ void stcs_d4(void* ptr, const D4& v) {
 
 constexpr int kQuadSamples = 128;  // samples per group
 
+// CTA size limit of the quad kernel: 640 threads = 20 resident warps per SM at 96 registers.  Measured on B200
+// (C3, profiles/r01_quad_ab.txt): 16 warps at 128 registers 77 % of the measured HBM peak, 20 warps at 96
+// registers 80.5 %, 24 warps at 80 registers 62 % (spills).
+#ifndef MCDP_QUAD_MAX_THREADS
+#define MCDP_QUAD_MAX_THREADS 640
+#endif
+
 // what MCDP_OPT_SAMPLES_PER_LANE = 0 (auto) selects
 #ifndef MCDP_AUTO_SPL
 #define MCDP_AUTO_SPL 4
 #endif
 
 template <int MODE, bool SMEM, bool DYN>
-__global__ void __launch_bounds__(MCDP_MAX_THREADS, 1) quad_sweep_kernel(const __grid_constant__ SweepParams p) {
+__global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(const __grid_constant__ SweepParams p) {
     constexpr bool kReduced = MODE == kModeReduced || MODE == kModeAttr;
     extern __shared__ __align__(128) unsigned char smem_dyn[];
     // dynamic shared memory as in chunk_sweep_kernel: [log table][DistRec[] + table pool (SMEM)][per-warp chunk rings]
