@@ -68,6 +68,19 @@ __device__ __forceinline__ void emp_value4(typename Mem<SMEM>::ptr guide_b, type
     for (int i = 0; i < 4; ++i) v[i] = Mem<SMEM>::f64(cp_b + off[i] + len8);
 }
 
+// x[0] > m || ... || x[3] > m as four compares and a predicate OR.  Written in PTX because the C form is folded into
+// max(x0..x3) > m, and fp64 max is a three-instruction NaN-propagating sequence on sm_100 (25 instructions in all).
+__device__ __forceinline__ bool any_gt4(const double (&x)[4], double m) {
+    uint32_t r;
+    asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+        "setp.gt.f64 p0, %1, %5;\n\tsetp.gt.f64 p1, %2, %5;\n\tsetp.gt.f64 p2, %3, %5;\n\tsetp.gt.f64 p3, %4, %5;\n\t"
+        "or.pred p0, p0, p1;\n\tor.pred p2, p2, p3;\n\tor.pred p0, p0, p2;\n\t"
+        "selp.u32 %0, 1, 0, p0;\n\t}"
+        : "=r"(r)
+        : "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(x[3]), "d"(m));
+    return r != 0u;
+}
+
 // erlang_value for four samples: ONE switch on the warp-uniform variant
 template <bool SMEM>
 __device__ __forceinline__ void erlang_value4(const DistView<SMEM>& d, int variant, const uint32_t (&w0)[4],
@@ -140,10 +153,10 @@ __device__ __forceinline__ void erlang_variate4(const DistView<SMEM>& d, const S
     uint32_t j[4] = {0u, 0u, 0u, 0u};
     erlang_draw4<SMEM>(d, variant, sd, true, j, act, key0, log_tab, x);
     // truncation (_core.cpp:98-104): draws 1, 2, ... until x <= max_scale; rare, so off the straight path
-    bool need[4];
+    if (__any_sync(0xFFFFFFFFu, any_gt4(x, mx))) {
+        bool need[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) need[i] = x[i] > mx;
-    if (__any_sync(0xFFFFFFFFu, need[0] || need[1] || need[2] || need[3])) {
+        for (int i = 0; i < 4; ++i) need[i] = x[i] > mx;
         do {
 #pragma unroll
             for (int i = 0; i < 4; ++i) j[i] += need[i] ? 1u : 0u;
