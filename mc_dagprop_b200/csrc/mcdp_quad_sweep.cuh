@@ -268,38 +268,39 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
             }
             const uint32_t act = uint32_t(q0.y);
             const double base = __hiloint2double(q0.w, q0.z);
-            double d[4];
-            if constexpr (MODE == kModeInjected) {
-                D4 dd{0.0, 0.0, 0.0, 0.0};
-                if (act != kNoAct) dd = ldcs_d4(f64_row(dur_base, act));
-                d[0] = dd.x;
-                d[1] = dd.y;
-                d[2] = dd.z;
-                d[3] = dd.w;
-            } else {
-                if (kind == kKindNone) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) d[i] = base;  // _core.cpp:304-305,325
-                } else {
-                    double e[4];
-                    sample_extra4<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, sd, key0, log_tab, e);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) d[i] = __dadd_rn(base, e[i]);  // _core.cpp:328
-                }
+            // duration known: stream it out (full mode) and apply the recurrence, _core.cpp:341-346
+            auto apply = [&](const double (&d)[4]) {
                 if constexpr (MODE == kModeFull) {
                     if (act != kNoAct) stcs_d4(f64_row(dur_base, act), D4{d[0], d[1], d[2], d[3]});
                 }
-            }
-            // _core.cpp:341-346
-            const int src_event = MODE == kModeAttr ? (act == kNoAct ? -3 : int(act)) : q0.x;
-            const double rsv[4] = {rs.x, rs.y, rs.z, rs.w};
+                const int src_event = MODE == kModeAttr ? (act == kNoAct ? -3 : int(act)) : q0.x;
+                const double rsv[4] = {rs.x, rs.y, rs.z, rs.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double t = ref_min(__dadd_rn(rsv[i], d[i]), ub);
-                if (t >= lat[i]) {
-                    lat[i] = t;
-                    cause[i] = src_event;
+                for (int i = 0; i < 4; ++i) {
+                    const double t = ref_min(__dadd_rn(rsv[i], d[i]), ub);
+                    if (t >= lat[i]) {
+                        lat[i] = t;
+                        cause[i] = src_event;
+                    }
                 }
+            };
+            if constexpr (MODE == kModeInjected) {
+                D4 dd{0.0, 0.0, 0.0, 0.0};
+                if (act != kNoAct) dd = ldcs_d4(f64_row(dur_base, act));
+                const double d[4] = {dd.x, dd.y, dd.z, dd.w};
+                apply(d);
+            } else if (kind == kKindNone) {
+                // _core.cpp:304-305,325.  A path of its own down to the recurrence: as a two-way merge in front of a
+                // shared tail, the four register copies of `base` were hoisted above the kind dispatch and cost every
+                // sampled entry 8 instructions.
+                const double d[4] = {base, base, base, base};
+                apply(d);
+            } else {
+                double e[4], d[4];
+                sample_extra4<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, sd, key0, log_tab, e);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) d[i] = __dadd_rn(base, e[i]);  // _core.cpp:328
+                apply(d);
             }
         }
         if (open && remaining == 0u) finalize();
