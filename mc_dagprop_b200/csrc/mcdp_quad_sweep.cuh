@@ -118,8 +118,10 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
     }
     sd.quad = ((sd.s[0] & 1u) == 0u) && sd.s[1] == sd.s[0] + 1u && sd.s[2] == sd.s[0] + 2u && sd.s[3] == sd.s[0] + 3u;
     const uint32_t lane_off = uint32_t(s0) * 8u;
+    uint64_t lane_off64 = lane_off;  // kept as a register pair: the 64-bit addend of the row multiply-add
+    asm volatile("" : "+l"(lane_off64));
     auto f64_row = [&](const void* base, uint32_t row) -> char* {
-        return const_cast<char*>(reinterpret_cast<const char*>(base)) + (uint64_t(row) * p.ldb8 + lane_off);
+        return const_cast<char*>(reinterpret_cast<const char*>(base)) + (uint64_t(row) * p.ldb8 + lane_off64);
     };
     auto i32_row = [&](const void* base, uint32_t row) -> char* {
         return const_cast<char*>(reinterpret_cast<const char*>(base)) + (uint64_t(row) * p.ldb4 + (lane_off >> 1));
