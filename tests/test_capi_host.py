@@ -169,3 +169,22 @@ def test_launch_shape_of_both_kernels():
     assert plan.launch_shape(1 << 15, reduced=True, n_bins=64)["samples_per_lane"] == 4
     with pytest.raises(RuntimeError, match="samples per lane"):
         plan.set_option(capi.OPT_SAMPLES_PER_LANE, 3)
+
+
+def test_library_is_sm_100a_code_with_bulk_copies_and_256_bit_accesses():
+    """What the build claims, read from the shipped binary (no GPU needed): one sm_100a cubin, the TMA bulk copy that
+    feeds the per-warp record ring (UBLKCP) with its mbarrier waits (SYNCS), and the 256-bit row loads / stores of the
+    quad kernel (LDG.E...256 / STG.E...256, new with sm_100)."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    elfs = subprocess.run([cuobjdump, "-lelf", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in elfs and not re.search(r"sm_(?!100a)\d+", elfs), elfs
+    sass = subprocess.run([cuobjdump, "-sass", "-fun", "quad_sweep_kernel", capi.LIB_PATH], capture_output=True, text=True).stdout
+    if "Function" not in sass:  # older cuobjdump: no -fun filter on mangled substrings
+        sass = subprocess.run([cuobjdump, "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "quad_sweep_kernel" in sass and "UBLKCP" in sass and "SYNCS" in sass
+    assert re.search(r"LDG\.E[.\w]*\.256", sass) and re.search(r"STG\.E[.\w]*\.256", sass)
