@@ -188,3 +188,30 @@ def test_library_is_sm_100a_code_with_bulk_copies_and_256_bit_accesses():
         sass = subprocess.run([cuobjdump, "-sass", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "quad_sweep_kernel" in sass and "UBLKCP" in sass and "SYNCS" in sass
     assert re.search(r"LDG\.E[.\w]*\.256", sass) and re.search(r"STG\.E[.\w]*\.256", sass)
+
+
+@pytest.mark.parametrize("gen", ["c1_toy", "c2_layered", "c5_deep_chain"])
+def test_launch_shape_invariants(gen):
+    """Whatever the options, a launch covers every sample, respects the CTA limits of its kernel (512 threads pair,
+    640 quad), keeps its named-barrier ids within the 15 a CTA has, and fits the SM's shared memory."""
+    dag, d = getattr(synth, gen)()
+    plan = capi.Plan(dag, d, device=capi.DEVICE_NONE)
+    rng = np.random.default_rng(1)
+    ns = [1, 63, 64, 65, 127, 128, 129, 18944, 1 << 15, 1 << 18, 1 << 20] + rng.integers(1, 1 << 21, size=20).tolist()
+    for spl in (0, 2, 4):
+        for wpg, gpc in [(0, 0), (1, 0), (3, 0), (16, 0), (20, 0), (0, 3), (5, 2), (8, 15), (20, 15)]:
+            plan.set_option(capi.OPT_SAMPLES_PER_LANE, spl)
+            plan.set_option(capi.OPT_WARPS_PER_GROUP, wpg)
+            plan.set_option(capi.OPT_GROUPS_PER_CTA, gpc)
+            for n in ns:
+                for reduced in (False, True):
+                    s = plan.launch_shape(n, reduced, 64 if reduced else 0)
+                    k = s["samples_per_lane"]
+                    assert k in (2, 4) and (spl == 0 or k == spl or s["batches"] > 1)
+                    assert s["threads"] == 32 * s["warps_per_group"] * s["groups_per_cta"]
+                    assert s["threads"] <= (640 if k == 4 else 512) and 1 <= s["groups_per_cta"] <= 15
+                    assert s["grid"] * s["groups_per_cta"] * 32 * k * s["batches"] >= n
+                    assert (s["grid"] - 1) * s["groups_per_cta"] * 32 * k * s["batches"] < n  # no empty CTA
+                    assert s["smem_bytes"] <= 227 * 1024
+                    if s["batches"] > 1:
+                        assert reduced and k == 2
