@@ -186,24 +186,15 @@ __global__ void __launch_bounds__(MCDP_MAX_THREADS, MCDP_MIN_BLOCKS)
             // atomic per statistic (and per distinct histogram bin) per warp
             const double xa = valid_a ? ra - ev_earliest : 0.0;
             const double xb = valid_b ? rb - ev_earliest : 0.0;
-            if (p.sum) {
-                const double t = warp_sum(xa + xb);
-                if (lane == 0) atomicAdd(p.sum + ev, t);
-            }
-            if (p.sumsq) {
-                const double t = warp_sum(xa * xa + xb * xb);
-                if (lane == 0) atomicAdd(p.sumsq + ev, t);
-            }
+            uint32_t late_packed = 0u;
             if (p.late) {
 #pragma unroll
                 for (int t = 0; t < MCDP_MAX_THRESHOLDS; ++t) {
-                    if (t < p.n_thresholds) {
-                        const int cnt = __reduce_add_sync(
-                            0xFFFFFFFFu, int(valid_a && xa > p.thresholds[t]) + int(valid_b && xb > p.thresholds[t]));
-                        if (lane == 0 && cnt) atomicAdd(p.late + size_t(t) * p.E + ev, (unsigned long long)cnt);
-                    }
+                    if (t < p.n_thresholds)
+                        late_packed |= (uint32_t(valid_a && xa > p.thresholds[t]) + uint32_t(valid_b && xb > p.thresholds[t])) << (8 * t);
                 }
             }
+            flush_sums(p, ev, lane, xa + xb, xa * xa + xb * xb, late_packed);
             if (p.hist) {
                 const int nb = p.n_bins;
                 int ba = min(max(int(floor((xa - p.hist_lo) * p.hist_scale)), 0), nb - 1);

@@ -188,27 +188,21 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
             double x[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) x[i] = valid[i] ? r[i] - ev_earliest : 0.0;
-            if (p.sum) {
-                const double t = warp_sum((x[0] + x[1]) + (x[2] + x[3]));
-                if (lane == 0) atomicAdd(p.sum + ev, t);
-            }
-            if (p.sumsq) {
-                const double t = warp_sum((x[0] * x[0] + x[1] * x[1]) + (x[2] * x[2] + x[3] * x[3]));
-                if (lane == 0) atomicAdd(p.sumsq + ev, t);
-            }
+            uint32_t late_packed = 0u;
             if (p.late) {
 #pragma unroll
                 for (int t = 0; t < MCDP_MAX_THRESHOLDS; ++t) {
                     if (t < p.n_thresholds) {
                         const double th = p.thresholds[t];
-                        int c = 0;
+                        uint32_t c = 0u;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) c += int(valid[i] && x[i] > th);
-                        const int cnt = __reduce_add_sync(0xFFFFFFFFu, c);
-                        if (lane == 0 && cnt) atomicAdd(p.late + size_t(t) * p.E + ev, (unsigned long long)cnt);
+                        for (int i = 0; i < 4; ++i) c += uint32_t(valid[i] && x[i] > th);
+                        late_packed |= c << (8 * t);
                     }
                 }
             }
+            flush_sums(p, ev, lane, (x[0] + x[1]) + (x[2] + x[3]), (x[0] * x[0] + x[1] * x[1]) + (x[2] * x[2] + x[3] * x[3]),
+                       late_packed);
             if (p.hist) {
                 const int nb = p.n_bins;
                 uint32_t* h = p.hist + size_t(ev) * nb;

@@ -75,6 +75,37 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Warp totals of s and q with ONE butterfly: after the first exchange the lower half-warp carries s, the upper
+// half-warp q.  Lanes 0-15 return the total of s, lanes 16-31 the total of q.
+__device__ __forceinline__ double warp_sum2(double s, double q, int lane) {
+    const bool upper = lane & 16;
+    const double give = upper ? s : q, keep = upper ? q : s;
+    double v = keep + __shfl_xor_sync(0xFFFFFFFFu, give, 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    return v;
+}
+
+// Per-event statistics that are sums over the warp's samples (reduced modes).  `s` / `q`: this lane's sum of delays
+// and of squared delays; `late_packed`: this lane's exceedance counts, 8 bits per threshold (a warp holds at most 128
+// samples, so the fields of the warp total cannot carry into each other).  One butterfly, one REDUX, and the atomics
+// of the thresholds issued by different lanes of one instruction.
+template <typename P>
+__device__ __forceinline__ void flush_sums(const P& p, uint32_t ev, int lane, double s, double q, uint32_t late_packed) {
+    if (p.sum || p.sumsq) {
+        const double t = warp_sum2(s, q, lane);
+        if (lane == 0 && p.sum) atomicAdd(p.sum + ev, t);
+        if (lane == 16 && p.sumsq) atomicAdd(p.sumsq + ev, t);
+    }
+    if (p.late) {
+        const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, late_packed);
+        if (lane < p.n_thresholds) {
+            const uint32_t cnt = (tot >> (8 * lane)) & 0xFFu;
+            if (cnt) atomicAdd(p.late + size_t(lane) * p.E + ev, (unsigned long long)cnt);
+        }
+    }
+}
+
 // std::min(a, b) of the reference build: (b < a) ? b : a  -- NOT fmin (NaN / signed-zero differ).
 __device__ __forceinline__ double ref_min(double a, double b) { return (b < a) ? b : a; }
 
