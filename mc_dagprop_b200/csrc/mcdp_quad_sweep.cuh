@@ -47,6 +47,13 @@ constexpr int kQuadSamples = 128;  // samples per group
 #define MCDP_QUAD_MAX_THREADS 640
 #endif
 
+// Unroll factor of the unit loop.  1 ships.  2 lets the two register sets of the one-unit-ahead gather alternate
+// instead of being copied (8 moves per unit) at twice the loop's code size: an experiment for the next round.
+#ifndef MCDP_QUAD_UNIT_UNROLL
+#define MCDP_QUAD_UNIT_UNROLL 1
+#endif
+constexpr int kQuadUnitUnroll = MCDP_QUAD_UNIT_UNROLL;
+
 // what MCDP_OPT_SAMPLES_PER_LANE = 0 (auto) selects
 #ifndef MCDP_AUTO_SPL
 #define MCDP_AUTO_SPL 4
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
         }
     };
     auto process = [&](uint32_t buf, int u0, uint32_t remaining) {
-#pragma unroll 1
+#pragma unroll kQuadUnitUnroll
         for (int u = u0; u < kChunkUnits; ++u) {
             const int4 q0 = lds128(buf + uint32_t(u) * 32u);
             const int4 q1 = lds128(buf + uint32_t(u) * 32u + 16u);
