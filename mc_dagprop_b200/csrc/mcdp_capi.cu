@@ -1,6 +1,7 @@
 // mcdp_capi.cu -- the C ABI of include/mcdp_b200.h: plan upload, kernel launches, and the
 // chunked host-buffer calls.  No torch types, no exceptions across the boundary, no CPU fallback.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -9,6 +10,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/mcdp_b200.h"
@@ -36,6 +38,25 @@ int32_t fail(int32_t code, const std::string& msg) {
         if (_e != cudaSuccess)                                                                      \
             return fail(MCDP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
     } while (0)
+
+// like MCDP_CUDA inside a chunk loop: record the failure and leave the loop, so that the code behind the loop
+// still drains the streams (copies into caller memory may be in flight)
+#define MCDP_CUDA_BRK(expr)                                                                         \
+    {                                                                                               \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            rc = fail(MCDP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+            break;                                                                                  \
+        }                                                                                           \
+    }
+
+// NVTX range (plan compile / H2D / kernel / D2H / reduce); a no-op unless a tool is attached
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct DeviceGuard {
     int prev = -1;
@@ -143,9 +164,64 @@ struct mcdp_plan {
     DevBuf<uint32_t> d_stat_u32;
     std::mutex stream_mu;  // lazy construction of the chunk streams
     std::mutex mu;  // instances are not re-entrant in the reference either; serialise instead of corrupting scratch
+    // largest dynamic shared memory size each kernel has been opted in for on this plan's device
+    std::mutex attr_mu;
+    std::unordered_map<const void*, size_t> smem_attr;
+    bool holds_l2_carveout = false;
 
-    ~mcdp_plan() {
+    ~mcdp_plan();
+};
+
+namespace {
+
+// The persisting-L2 carve-out is a device-wide limit: plans on one device share it.  It only ever grows while plans
+// are alive (the largest record stream decides) and the device's original limit comes back with the last plan.
+struct L2Carveout {
+    std::mutex mu;
+    struct PerDevice {
+        int plans = 0;
+        size_t original = 0, current = 0;
+    };
+    std::unordered_map<int, PerDevice> dev;
+    size_t acquire(int device, size_t want) {
+        std::lock_guard<std::mutex> lock(mu);
+        PerDevice& d = dev[device];
+        if (d.plans == 0) {
+            if (cudaDeviceGetLimit(&d.original, cudaLimitPersistingL2CacheSize) != cudaSuccess) {
+                cudaGetLastError();
+                d.original = 0;
+            }
+            d.current = d.original;
+        }
+        ++d.plans;
+        if (want > d.current) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+                d.current = want;
+            else
+                cudaGetLastError();
+        }
+        return d.current;
+    }
+    void release(int device) {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = dev.find(device);
+        if (it == dev.end() || it->second.plans == 0) return;
+        if (--it->second.plans == 0) {
+            cudaCtxResetPersistingL2Cache();
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, it->second.original);
+            cudaGetLastError();
+            dev.erase(it);
+        }
+    }
+};
+L2Carveout g_l2;
+
+}  // namespace
+
+mcdp_plan::~mcdp_plan() {
+    {
         DeviceGuard g(device);
+        if (holds_l2_carveout) g_l2.release(device);
         for (auto& s : slots) s.release();
         for (auto& a : streams)
             for (auto& st : a) {
@@ -165,7 +241,7 @@ struct mcdp_plan {
         d_stat_u64.release();
         d_stat_u32.release();
     }
-};
+}
 
 namespace {
 
@@ -297,7 +373,15 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false,
 template <typename K>
 int32_t launch_kernel(mcdp_plan* plan, K k, const SweepParams& p, const LaunchShape& s, size_t smem, const void* stream_base,
                       size_t stream_bytes, cudaStream_t stream) {
-    if (smem > 48 * 1024) MCDP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    if (smem > 48 * 1024) {
+        // opt in once per kernel and size (not on every launch)
+        std::lock_guard<std::mutex> lock(plan->attr_mu);
+        size_t& have = plan->smem_attr[reinterpret_cast<const void*>(k)];
+        if (smem > have) {
+            MCDP_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            have = smem;
+        }
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(s.grid);
     cfg.blockDim = dim3(unsigned(s.threads));
@@ -526,6 +610,7 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
     if (!plan) return fail(MCDP_ERR_ARG, "out of host memory");
     std::string err;
     bool ok = false;
+    NvtxRange nvtx_compile("mcdp:plan compile");
     try {
         ok = compile_plan(*graph, *dists, plan->host, err);
     } catch (const std::exception& e) {
@@ -554,10 +639,6 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
         return fail(MCDP_ERR_ARG, "device ordinal out of range");
     }
     plan->device = device;
-    if (const char* e = std::getenv("MCDP_SAMPLES_PER_LANE")) {  // process-wide default (A/B runs of whole test suites)
-        const int v = std::atoi(e);
-        if (v == 2 || v == 4) plan->samples_per_lane = v;
-    }
     DeviceGuard guard(device);
     if (!guard.ok) {
         delete plan;
@@ -568,16 +649,17 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
         plan->sm_count = prop.multiProcessorCount;
         plan->smem_optin = prop.sharedMemPerBlockOptin;
         plan->l2_window_max = size_t(std::max(prop.accessPolicyMaxWindowSize, 0));
-        // set aside L2 for the record stream (device-wide limit; the last plan created decides)
+        // set aside L2 for the record stream (a device-wide limit shared by the plans of this device: see L2Carveout)
         const size_t stream_bytes = plan->host.units.size() * sizeof(ChunkUnit);
         const size_t want = std::min<size_t>({stream_bytes + (stream_bytes >> 3) + (1u << 20),
                                              size_t(std::max(prop.persistingL2CacheMaxSize, 0)), size_t(64) << 20});
-        if (want > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
-            plan->l2_persist_bytes = want;
-        else
-            cudaGetLastError();
+        if (want > 0) {
+            plan->l2_persist_bytes = std::min(g_l2.acquire(device, want), want);
+            plan->holds_l2_carveout = true;
+        }
     }
     const HostPlan& h = plan->host;
+    NvtxRange nvtx_upload("mcdp:plan H2D");
     int32_t rc = upload(plan->d_level_begin, h.level_begin);
     if (!rc) rc = upload(plan->d_orphans, h.orphans);
     if (!rc) rc = upload(plan->d_dists, h.dists);
@@ -745,10 +827,14 @@ int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t
     return mcdp_run_attribution_device(plan, d_seeds, seed0, n, desc, d_sum, d_sumsq, d_late, d_hist, nullptr, nullptr, stream);
 }
 
-int32_t mcdp_run_attribution_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n,
-                                    const mcdp_stats_desc* desc, double* d_sum, double* d_sumsq,
-                                    unsigned long long* d_late, uint32_t* d_hist, unsigned long long* d_cause_act,
-                                    unsigned long long* d_cause_none, void* stream) {
+}  // extern "C"
+
+namespace {
+// plan->mu must be held by the caller (the device entry point and the host entry point both take it for the whole call)
+int32_t run_attribution_locked(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n,
+                               const mcdp_stats_desc* desc, double* d_sum, double* d_sumsq,
+                               unsigned long long* d_late, uint32_t* d_hist, unsigned long long* d_cause_act,
+                               unsigned long long* d_cause_none, void* stream) {
     if (!plan || !desc) return fail(MCDP_ERR_ARG, "null argument");
     const bool attr = d_cause_act != nullptr || d_cause_none != nullptr;
     if (attr && (!d_cause_act || !d_cause_none)) return fail(MCDP_ERR_ARG, "cause_act and cause_none go together");
@@ -758,8 +844,8 @@ int32_t mcdp_run_attribution_device(mcdp_plan* plan, const int32_t* d_seeds, int
     if (desc->n_thresholds < 0 || desc->n_thresholds > MCDP_MAX_THRESHOLDS) return fail(MCDP_ERR_ARG, "n_thresholds must be 0..4");
     if (desc->n_bins < 0 || desc->n_bins > 1024) return fail(MCDP_ERR_ARG, "n_bins must be 0..1024");
     if (d_hist && desc->n_bins > 0 && !(desc->hist_hi > desc->hist_lo)) return fail(MCDP_ERR_ARG, "hist_hi must exceed hist_lo");
-    std::lock_guard<std::mutex> lock(plan->mu);
     DeviceGuard guard(plan->device);
+    NvtxRange nvtx("mcdp:reduced sweep");
     int32_t rc = ensure_reduced_stream(plan);
     if (rc) return rc;
     const HostPlan& h = plan->host;
@@ -798,6 +884,19 @@ int32_t mcdp_run_attribution_device(mcdp_plan* plan, const int32_t* d_seeds, int
         if (rc) return rc;
     }
     return MCDP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t mcdp_run_attribution_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n,
+                                    const mcdp_stats_desc* desc, double* d_sum, double* d_sumsq,
+                                    unsigned long long* d_late, uint32_t* d_hist, unsigned long long* d_cause_act,
+                                    unsigned long long* d_cause_none, void* stream) {
+    if (!plan || !desc) return fail(MCDP_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(plan->mu);
+    return run_attribution_locked(plan, d_seeds, seed0, n, desc, d_sum, d_sumsq, d_late, d_hist, d_cause_act, d_cause_none,
+                                  stream);
 }
 
 int32_t mcdp_transpose_f64_device(const double* d_in, int64_t rows, int64_t n, int64_t ld, double* d_out, void* stream) {
@@ -840,14 +939,18 @@ int32_t mcdp_run_many_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, dou
     for (int64_t off = 0; off < n && !rc; off += chunk, ++idx) {
         HostSlot& sl = plan->slots[idx & 1];
         const int64_t m = std::min(chunk, n - off);
-        if (!sl.stream) MCDP_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        if (!sl.stream) MCDP_CUDA_BRK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
         // a slot is reused every other chunk: its previous copies must have drained
-        MCDP_CUDA(cudaStreamSynchronize(sl.stream));
-        MCDP_CUDA(sl.seeds.ensure(size_t(chunk)));
-        MCDP_CUDA(sl.realized.ensure(size_t(E) * size_t(chunk)));
-        MCDP_CUDA(sl.durations.ensure(size_t(A) * size_t(chunk)));
-        MCDP_CUDA(sl.cause.ensure(size_t(E) * size_t(chunk)));
-        MCDP_CUDA(cudaMemcpyAsync(sl.seeds.p, seeds + off, size_t(m) * 4, cudaMemcpyHostToDevice, sl.stream));
+        MCDP_CUDA_BRK(cudaStreamSynchronize(sl.stream));
+        MCDP_CUDA_BRK(sl.seeds.ensure(size_t(chunk)));
+        MCDP_CUDA_BRK(sl.realized.ensure(size_t(E) * size_t(chunk)));
+        MCDP_CUDA_BRK(sl.durations.ensure(size_t(A) * size_t(chunk)));
+        MCDP_CUDA_BRK(sl.cause.ensure(size_t(E) * size_t(chunk)));
+        {
+            NvtxRange nvtx("mcdp:seeds H2D");
+            MCDP_CUDA_BRK(cudaMemcpyAsync(sl.seeds.p, seeds + off, size_t(m) * 4, cudaMemcpyHostToDevice, sl.stream));
+        }
+        NvtxRange nvtx_chunk("mcdp:chunk sweep + transpose + D2H");
         const LaunchShape s = choose_shape(plan, m);
         SweepParams p = base_params(plan, s, m, chunk);
         p.seeds = sl.seeds.p;
@@ -856,8 +959,10 @@ int32_t mcdp_run_many_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, dou
         p.cause = sl.cause.p;
         if (plan->rng_stream == 1) {
             // the sampler's normal cache is plan-wide scratch: chunks of the compatible stream run one after another
+            cudaError_t ce = cudaSuccess;
             for (auto& other : plan->slots)
-                if (other.stream && other.stream != sl.stream) MCDP_CUDA(cudaStreamSynchronize(other.stream));
+                if (other.stream && other.stream != sl.stream && ce == cudaSuccess) ce = cudaStreamSynchronize(other.stream);
+            MCDP_CUDA_BRK(ce);
             rc = launch_compat_sampler(plan, sl.seeds.p, 0, m, sl.durations.p, chunk, sl.stream);
             if (rc) break;
             p.inj = sl.durations.p;
@@ -867,22 +972,22 @@ int32_t mcdp_run_many_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, dou
         }
         if (rc) break;
         if (realized && E) {
-            MCDP_CUDA(sl.t_realized.ensure(size_t(E) * size_t(chunk)));
+            MCDP_CUDA_BRK(sl.t_realized.ensure(size_t(E) * size_t(chunk)));
             rc = launch_transpose<double>(sl.realized.p, chunk, E, m, sl.t_realized.p, E, sl.stream);
             if (rc) break;
-            MCDP_CUDA(cudaMemcpyAsync(realized + off * E, sl.t_realized.p, size_t(m) * E * 8, cudaMemcpyDeviceToHost, sl.stream));
+            MCDP_CUDA_BRK(cudaMemcpyAsync(realized + off * E, sl.t_realized.p, size_t(m) * E * 8, cudaMemcpyDeviceToHost, sl.stream));
         }
         if (durations && A) {
-            MCDP_CUDA(sl.t_durations.ensure(size_t(A) * size_t(chunk)));
+            MCDP_CUDA_BRK(sl.t_durations.ensure(size_t(A) * size_t(chunk)));
             rc = launch_transpose<double>(sl.durations.p, chunk, A, m, sl.t_durations.p, A, sl.stream);
             if (rc) break;
-            MCDP_CUDA(cudaMemcpyAsync(durations + off * A, sl.t_durations.p, size_t(m) * A * 8, cudaMemcpyDeviceToHost, sl.stream));
+            MCDP_CUDA_BRK(cudaMemcpyAsync(durations + off * A, sl.t_durations.p, size_t(m) * A * 8, cudaMemcpyDeviceToHost, sl.stream));
         }
         if (cause && E) {
-            MCDP_CUDA(sl.t_cause.ensure(size_t(E) * size_t(chunk)));
+            MCDP_CUDA_BRK(sl.t_cause.ensure(size_t(E) * size_t(chunk)));
             rc = launch_transpose<int32_t>(sl.cause.p, chunk, E, m, sl.t_cause.p, E, sl.stream);
             if (rc) break;
-            MCDP_CUDA(cudaMemcpyAsync(cause + off * E, sl.t_cause.p, size_t(m) * E * 4, cudaMemcpyDeviceToHost, sl.stream));
+            MCDP_CUDA_BRK(cudaMemcpyAsync(cause + off * E, sl.t_cause.p, size_t(m) * E * 4, cudaMemcpyDeviceToHost, sl.stream));
         }
     }
     for (auto& sl : plan->slots)
@@ -909,14 +1014,14 @@ int32_t mcdp_run_injected_host(mcdp_plan* plan, const double* durations, int64_t
     for (int64_t off = 0; off < n && !rc; off += chunk, ++idx) {
         HostSlot& sl = plan->slots[idx & 1];
         const int64_t m = std::min(chunk, n - off);
-        if (!sl.stream) MCDP_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
-        MCDP_CUDA(cudaStreamSynchronize(sl.stream));
-        MCDP_CUDA(sl.realized.ensure(size_t(E) * size_t(chunk)));
-        MCDP_CUDA(sl.durations.ensure(size_t(A) * size_t(chunk)));
-        MCDP_CUDA(sl.t_durations.ensure(size_t(A) * size_t(chunk)));
-        MCDP_CUDA(sl.cause.ensure(size_t(E) * size_t(chunk)));
+        if (!sl.stream) MCDP_CUDA_BRK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+        MCDP_CUDA_BRK(cudaStreamSynchronize(sl.stream));
+        MCDP_CUDA_BRK(sl.realized.ensure(size_t(E) * size_t(chunk)));
+        MCDP_CUDA_BRK(sl.durations.ensure(size_t(A) * size_t(chunk)));
+        MCDP_CUDA_BRK(sl.t_durations.ensure(size_t(A) * size_t(chunk)));
+        MCDP_CUDA_BRK(sl.cause.ensure(size_t(E) * size_t(chunk)));
         if (A) {
-            MCDP_CUDA(cudaMemcpyAsync(sl.t_durations.p, durations + off * A, size_t(m) * A * 8, cudaMemcpyHostToDevice, sl.stream));
+            MCDP_CUDA_BRK(cudaMemcpyAsync(sl.t_durations.p, durations + off * A, size_t(m) * A * 8, cudaMemcpyHostToDevice, sl.stream));
             // [m][A] sample-major -> [A][chunk] event-major
             rc = launch_transpose<double>(sl.t_durations.p, A, m, A, sl.durations.p, chunk, sl.stream);
             if (rc) break;
@@ -929,16 +1034,16 @@ int32_t mcdp_run_injected_host(mcdp_plan* plan, const double* durations, int64_t
         rc = launch_sweep<kModeInjected>(plan, p, s, sl.stream);
         if (rc) break;
         if (realized && E) {
-            MCDP_CUDA(sl.t_realized.ensure(size_t(E) * size_t(chunk)));
+            MCDP_CUDA_BRK(sl.t_realized.ensure(size_t(E) * size_t(chunk)));
             rc = launch_transpose<double>(sl.realized.p, chunk, E, m, sl.t_realized.p, E, sl.stream);
             if (rc) break;
-            MCDP_CUDA(cudaMemcpyAsync(realized + off * E, sl.t_realized.p, size_t(m) * E * 8, cudaMemcpyDeviceToHost, sl.stream));
+            MCDP_CUDA_BRK(cudaMemcpyAsync(realized + off * E, sl.t_realized.p, size_t(m) * E * 8, cudaMemcpyDeviceToHost, sl.stream));
         }
         if (cause && E) {
-            MCDP_CUDA(sl.t_cause.ensure(size_t(E) * size_t(chunk)));
+            MCDP_CUDA_BRK(sl.t_cause.ensure(size_t(E) * size_t(chunk)));
             rc = launch_transpose<int32_t>(sl.cause.p, chunk, E, m, sl.t_cause.p, E, sl.stream);
             if (rc) break;
-            MCDP_CUDA(cudaMemcpyAsync(cause + off * E, sl.t_cause.p, size_t(m) * E * 4, cudaMemcpyDeviceToHost, sl.stream));
+            MCDP_CUDA_BRK(cudaMemcpyAsync(cause + off * E, sl.t_cause.p, size_t(m) * E * 4, cudaMemcpyDeviceToHost, sl.stream));
         }
     }
     for (auto& sl : plan->slots)
@@ -964,50 +1069,54 @@ int32_t mcdp_run_attribution_host(mcdp_plan* plan, const int32_t* seeds, int64_t
     if (attr && (!cause_act || !cause_none)) return fail(MCDP_ERR_ARG, "cause_act and cause_none go together");
     const int64_t E = plan->host.E, A = plan->host.A;
     const int64_t nt = std::max(desc->n_thresholds, 0), nb = std::max(desc->n_bins, 0);
-    double* d_sum = nullptr;
-    double* d_sumsq = nullptr;
-    unsigned long long* d_late = nullptr;
+    // One call at a time per plan, from the sizing of the shared accumulators to the last copy-back: two threads on
+    // one propagator would otherwise sum into each other's statistics (the binding releases the GIL here).
+    std::lock_guard<std::mutex> lock(plan->mu);
+    DeviceGuard guard(plan->device);
+    HostSlot& sl = plan->slots[0];
+    if (!sl.stream) MCDP_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+    cudaStream_t st = sl.stream;
+    MCDP_CUDA(plan->d_stat_f64.ensure(size_t(2 * E)));
+    MCDP_CUDA(plan->d_stat_u64.ensure(size_t(nt * E) + (attr ? size_t(A + E) : 0)));
+    MCDP_CUDA(plan->d_stat_u32.ensure(size_t(nb * E)));
+    MCDP_CUDA(sl.seeds.ensure(size_t(std::max<int64_t>(n, 1))));
+    double* d_sum = plan->d_stat_f64.p;
+    double* d_sumsq = d_sum + E;
+    unsigned long long* d_late = plan->d_stat_u64.p;
+    uint32_t* d_hist = plan->d_stat_u32.p;
     unsigned long long* d_cause_act = nullptr;
     unsigned long long* d_cause_none = nullptr;
-    uint32_t* d_hist = nullptr;
-    int32_t* d_seeds = nullptr;
-    {
-        std::lock_guard<std::mutex> lock(plan->mu);
-        DeviceGuard guard(plan->device);
-        MCDP_CUDA(plan->d_stat_f64.ensure(size_t(2 * E)));
-        MCDP_CUDA(plan->d_stat_u64.ensure(size_t(nt * E) + (attr ? size_t(A + E) : 0)));
-        MCDP_CUDA(plan->d_stat_u32.ensure(size_t(nb * E)));
-        MCDP_CUDA(plan->slots[0].seeds.ensure(size_t(std::max<int64_t>(n, 1))));
-        d_sum = plan->d_stat_f64.p;
-        d_sumsq = d_sum + E;
-        d_late = plan->d_stat_u64.p;
-        d_hist = plan->d_stat_u32.p;
-        d_seeds = plan->slots[0].seeds.p;
-        MCDP_CUDA(cudaMemset(d_sum, 0, size_t(2 * E) * 8));
-        if (nt) MCDP_CUDA(cudaMemset(d_late, 0, size_t(nt * E) * 8));
-        if (nb) MCDP_CUDA(cudaMemset(d_hist, 0, size_t(nb * E) * 4));
-        if (attr) {
-            d_cause_act = d_late + nt * E;
-            d_cause_none = d_cause_act + A;
-            MCDP_CUDA(cudaMemset(d_cause_act, 0, size_t(A + E) * 8));
+    int32_t rc = MCDP_OK;
+    do {
+        {
+            NvtxRange nvtx("mcdp:reduced H2D + clear");
+            if (E) MCDP_CUDA_BRK(cudaMemsetAsync(d_sum, 0, size_t(2 * E) * 8, st));
+            if (nt && E) MCDP_CUDA_BRK(cudaMemsetAsync(d_late, 0, size_t(nt * E) * 8, st));
+            if (nb && E) MCDP_CUDA_BRK(cudaMemsetAsync(d_hist, 0, size_t(nb * E) * 4, st));
+            if (attr) {
+                d_cause_act = d_late + nt * E;
+                d_cause_none = d_cause_act + A;
+                if (A + E) MCDP_CUDA_BRK(cudaMemsetAsync(d_cause_act, 0, size_t(A + E) * 8, st));
+            }
+            if (n) MCDP_CUDA_BRK(cudaMemcpyAsync(sl.seeds.p, seeds, size_t(n) * 4, cudaMemcpyHostToDevice, st));
         }
-        if (n) MCDP_CUDA(cudaMemcpy(d_seeds, seeds, size_t(n) * 4, cudaMemcpyHostToDevice));
-    }
-    int32_t rc = mcdp_run_attribution_device(plan, d_seeds, 0, n, desc, sum ? d_sum : nullptr, sumsq ? d_sumsq : nullptr,
-                                             late ? d_late : nullptr, hist ? d_hist : nullptr, d_cause_act, d_cause_none,
-                                             nullptr);
-    if (rc) return rc;
-    DeviceGuard guard(plan->device);
-    MCDP_CUDA(cudaDeviceSynchronize());
-    if (sum) MCDP_CUDA(cudaMemcpy(sum, d_sum, size_t(E) * 8, cudaMemcpyDeviceToHost));
-    if (sumsq) MCDP_CUDA(cudaMemcpy(sumsq, d_sumsq, size_t(E) * 8, cudaMemcpyDeviceToHost));
-    if (late && nt) MCDP_CUDA(cudaMemcpy(late, d_late, size_t(nt * E) * 8, cudaMemcpyDeviceToHost));
-    if (hist && nb) MCDP_CUDA(cudaMemcpy(hist, d_hist, size_t(nb * E) * 4, cudaMemcpyDeviceToHost));
-    if (attr) {
-        if (A) MCDP_CUDA(cudaMemcpy(cause_act, d_cause_act, size_t(A) * 8, cudaMemcpyDeviceToHost));
-        if (E) MCDP_CUDA(cudaMemcpy(cause_none, d_cause_none, size_t(E) * 8, cudaMemcpyDeviceToHost));
-    }
-    return MCDP_OK;
+        rc = run_attribution_locked(plan, sl.seeds.p, 0, n, desc, sum ? d_sum : nullptr, sumsq ? d_sumsq : nullptr,
+                                    late ? d_late : nullptr, hist ? d_hist : nullptr, d_cause_act, d_cause_none, st);
+        if (rc) break;
+        NvtxRange nvtx("mcdp:reduced D2H");
+        if (sum && E) MCDP_CUDA_BRK(cudaMemcpyAsync(sum, d_sum, size_t(E) * 8, cudaMemcpyDeviceToHost, st));
+        if (sumsq && E) MCDP_CUDA_BRK(cudaMemcpyAsync(sumsq, d_sumsq, size_t(E) * 8, cudaMemcpyDeviceToHost, st));
+        if (late && nt && E) MCDP_CUDA_BRK(cudaMemcpyAsync(late, d_late, size_t(nt * E) * 8, cudaMemcpyDeviceToHost, st));
+        if (hist && nb && E) MCDP_CUDA_BRK(cudaMemcpyAsync(hist, d_hist, size_t(nb * E) * 4, cudaMemcpyDeviceToHost, st));
+        if (attr) {
+            if (A) MCDP_CUDA_BRK(cudaMemcpyAsync(cause_act, d_cause_act, size_t(A) * 8, cudaMemcpyDeviceToHost, st));
+            if (E) MCDP_CUDA_BRK(cudaMemcpyAsync(cause_none, d_cause_none, size_t(E) * 8, cudaMemcpyDeviceToHost, st));
+        }
+    } while (false);
+    // always drain: copies into caller memory may be in flight even when a later step failed
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess && !rc) rc = fail(MCDP_ERR_CUDA, std::string("stream sync: ") + cudaGetErrorString(e));
+    return rc;
 }
 
 void* mcdp_host_alloc(size_t bytes) {

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include "mcdp_records.h"
+#include "mcdp_sampling.cuh"  // kGammaMaxAttempts: one attempt cap for both generator streams
 
 namespace mcdp {
 
@@ -113,9 +114,11 @@ __global__ void __launch_bounds__(128) compat_sample_kernel(const __grid_constan
                 case MCDP_DIST_EXPONENTIAL: {
                     const double rate = d.p[7];  // 1.0 / lambda, divided on the host like ExponentialDist's ctor
                     double x;
+                    uint32_t tries = 0u;  // the reference spins until x <= max_scale; capped like the Philox path
                     do {
                         x = __ddiv_rn(-log(__dadd_rn(1.0, -canonical(g))), rate);
-                    } while (x > d.p[1]);
+                    } while (x > d.p[1] && ++tries < kGammaMaxAttempts);
+                    if (x > d.p[1]) x = d.p[1];
                     extra = __dmul_rn(x, ar.base);
                     break;
                 }
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(128) compat_sample_kernel(const __grid_constan
                     double* cache = p.norm_cache + size_t(ar.dist) * p.ld + s;
                     bool cached = (cached_mask >> ar.dist) & 1ull;
                     double x;
+                    uint32_t tries = 0u;  // same cap for the truncation loop (a tiny max_scale would hang the device)
                     do {
                         double u, v, n;
                         do {
@@ -144,7 +148,8 @@ __global__ void __launch_bounds__(128) compat_sample_kernel(const __grid_constan
                             while (u == 0.0);
                             x = __dmul_rn(__dmul_rn(__dmul_rn(pow(u, __ddiv_rn(1.0, alpha)), a1), v), beta);
                         }
-                    } while (x > d.p[2]);
+                    } while (x > d.p[2] && ++tries < kGammaMaxAttempts);
+                    if (x > d.p[2]) x = d.p[2];
                     cached_mask = cached ? (cached_mask | (1ull << ar.dist)) : (cached_mask & ~(1ull << ar.dist));
                     extra = __dmul_rn(x, ar.base);
                     break;

@@ -9,10 +9,14 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <unistd.h>
+
 #include <cstdint>
+#include <cstdlib>
 #include <limits>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -59,19 +63,146 @@ struct DagContext {
         : events(std::move(ev)), activity_map(std::move(am)), precedence_list(std::move(pl)), max_delay(md) {}
 };
 
+// ---- result memory: pinned host blocks, recycled between calls -----------------------------------------
+// Results are written by DMA (mcdp_run_many_host).  Into pageable memory the driver stages every copy through
+// its own bounce buffers at a fraction of the PCIe rate, and a fresh std::vector adds a value-initialising pass
+// plus one page fault per 4 KB.  Blocks of >= 1 MiB therefore come from cudaHostAlloc (mcdp_host_alloc) and go
+// back to a size-bucketed free list when the last SimResult / array that views them dies, so a loop of
+// run_many calls pins its memory once.  Small blocks (run(seed) on a small DAG) are plain malloc.
+class HostPool {
+   public:
+    struct Block {
+        void* p = nullptr;
+        size_t cap = 0;
+        bool pinned = false;
+    };
+    static HostPool& instance() {
+        static HostPool* pool = new HostPool();  // leaked on purpose: blocks may outlive static destruction
+        return *pool;
+    }
+    Block take(size_t bytes) {
+        Block b;
+        if (bytes < kPinThreshold) {
+            b.p = std::malloc(bytes ? bytes : 1);
+            b.cap = bytes;
+            if (!b.p) throw std::bad_alloc();
+            return b;
+        }
+        const size_t cap = bucket(bytes);
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            auto it = free_.find(cap);
+            if (it != free_.end()) {
+                b = Block{it->second, cap, true};
+                free_.erase(it);
+                cached_ -= cap;
+                return b;
+            }
+        }
+        b.p = mcdp_host_alloc(cap);
+        b.cap = cap;
+        b.pinned = b.p != nullptr;
+        if (!b.p) {  // pinning refused (limits, no device): pageable memory still works, only slower
+            b.p = std::malloc(cap);
+            if (!b.p) throw std::bad_alloc();
+        }
+        return b;
+    }
+    void give(const Block& b) {
+        if (!b.p) return;
+        if (!b.pinned) {
+            std::free(b.p);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            if (cached_ + b.cap <= limit_) {
+                free_.emplace(b.cap, b.p);
+                cached_ += b.cap;
+                return;
+            }
+        }
+        mcdp_host_free(b.p);
+    }
+    void set_limit(size_t bytes) {
+        std::vector<void*> drop;
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            limit_ = bytes;
+            while (cached_ > limit_ && !free_.empty()) {
+                auto it = std::prev(free_.end());
+                drop.push_back(it->second);
+                cached_ -= it->first;
+                free_.erase(it);
+            }
+        }
+        for (void* p : drop) mcdp_host_free(p);
+    }
+    size_t limit() const { return limit_; }
+    size_t cached() const { return cached_; }
+
+   private:
+    static constexpr size_t kPinThreshold = size_t(1) << 20;
+    // sizes round up to 1/8 steps of their power of two: a slightly different seed count reuses the block
+    static size_t bucket(size_t bytes) {
+        size_t p2 = size_t(1) << 20;
+        while (p2 < bytes) p2 <<= 1;
+        const size_t step = p2 >> 4;
+        return (bytes + step - 1) / step * step;
+    }
+    HostPool() {
+        const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
+        const size_t ram = pages > 0 && psz > 0 ? size_t(pages) * size_t(psz) : size_t(64) << 30;
+        limit_ = std::min<size_t>(ram / 4, size_t(64) << 30);
+    }
+    std::mutex mu_;
+    std::multimap<size_t, void*> free_;
+    size_t cached_ = 0, limit_ = 0;
+};
+
 // ---- results: one shared batch, per-sample views (reference SimResult, _core.cpp:65-69) ----
+// All SimResult objects of one run_many call view ONE batch (a single DMA target): the batch lives until the last
+// of them is released.  A caller that keeps one result of a large batch for long should copy its arrays.
 struct SimBatch {
     size_t n = 0, E = 0, A = 0;
-    std::vector<double> realized, durations;
-    std::vector<int32_t> cause;
+    HostPool::Block block;
+    double* realized = nullptr;
+    double* durations = nullptr;
+    int32_t* cause = nullptr;
+    SimBatch(size_t n_, size_t E_, size_t A_) : n(n_), E(E_), A(A_) {
+        auto up = [](size_t b) { return (b + 63) & ~size_t(63); };
+        const size_t br = up(n * E * 8), bd = up(n * A * 8), bc = up(n * E * 4);
+        block = HostPool::instance().take(br + bd + bc);
+        char* base = static_cast<char*>(block.p);
+        realized = reinterpret_cast<double*>(base);
+        durations = reinterpret_cast<double*>(base + br);
+        cause = reinterpret_cast<int32_t*>(base + br + bd);
+    }
+    ~SimBatch() { HostPool::instance().give(block); }
+    SimBatch(const SimBatch&) = delete;
+    SimBatch& operator=(const SimBatch&) = delete;
 };
 struct SimResult {
     std::shared_ptr<SimBatch> batch;
     size_t row = 0;
-    double* realized() const { return batch->realized.data() + row * batch->E; }
-    double* durations() const { return batch->durations.data() + row * batch->A; }
-    int32_t* cause() const { return batch->cause.data() + row * batch->E; }
+    double* realized() const { return batch->realized + row * batch->E; }
+    double* durations() const { return batch->durations + row * batch->A; }
+    int32_t* cause() const { return batch->cause + row * batch->E; }
 };
+
+// a numpy array over a pooled block; the block returns to the pool when the array dies
+template <typename T>
+py::array_t<T> pooled_array(std::vector<py::ssize_t> shape) {
+    size_t count = 1;
+    for (auto d : shape) count *= size_t(d);
+    auto* blk = new HostPool::Block(HostPool::instance().take(count * sizeof(T)));
+    py::capsule owner(blk, [](void* q) {
+        auto* b = static_cast<HostPool::Block*>(q);
+        HostPool::instance().give(*b);
+        delete b;
+    });
+    return py::array_t<T>(shape, static_cast<T*>(blk->p), owner);
+}
 
 // ---- generator: parameter tables only; sampling happens on the device ----
 struct DistSpec {
@@ -233,16 +364,10 @@ class MonteCarloPropagator {
     }
 
     std::shared_ptr<SimBatch> run_batch(const std::vector<int>& seeds) {
-        auto b = std::make_shared<SimBatch>();
-        b->n = seeds.size();
-        b->E = size_t(node_count());
-        b->A = size_t(activity_count());
-        b->realized.resize(b->n * b->E);
-        b->durations.resize(b->n * b->A);
-        b->cause.resize(b->n * b->E);
+        auto b = std::make_shared<SimBatch>(seeds.size(), size_t(node_count()), size_t(activity_count()));
         static_assert(sizeof(int) == sizeof(int32_t), "seeds are C ints");
-        int32_t rc = mcdp_run_many_host(plan_, reinterpret_cast<const int32_t*>(seeds.data()), int64_t(b->n),
-                                        b->realized.data(), b->durations.data(), b->cause.data());
+        int32_t rc = mcdp_run_many_host(plan_, reinterpret_cast<const int32_t*>(seeds.data()), int64_t(b->n), b->realized,
+                                        b->durations, b->cause);
         if (rc != MCDP_OK) throw_last();
         return b;
     }
@@ -271,8 +396,8 @@ class MonteCarloPropagator {
     // additive: one [n,E] / [n,A] / [n,E] array triple instead of n SimResult objects
     py::tuple run_many_arrays(py::array_t<int32_t, py::array::c_style | py::array::forcecast> seeds) {
         const int64_t n = seeds.size(), E = node_count(), A = activity_count();
-        py::array_t<double> r({n, E}), d({n, A});
-        py::array_t<int32_t> c({n, E});
+        py::array_t<double> r = pooled_array<double>({n, E}), d = pooled_array<double>({n, A});
+        py::array_t<int32_t> c = pooled_array<int32_t>({n, E});
         int32_t rc;
         {
             py::gil_scoped_release release;
@@ -346,6 +471,11 @@ using namespace mcdp_py;
 
 PYBIND11_MODULE(_core, m) {
     m.doc() = "Core Monte-Carlo DAG-propagation simulator (B200 / sm_100a engine)";
+
+    m.def(
+        "set_pinned_cache_limit", [](size_t bytes) { HostPool::instance().set_limit(bytes); }, py::arg("bytes"),
+        "Upper bound on pinned result memory kept for reuse between calls (default: min(RAM / 4, 64 GiB)); 0 frees the cache");
+    m.def("pinned_cache_bytes", []() { return HostPool::instance().cached(); }, "Pinned result memory currently cached for reuse");
 
     py::class_<EventTimestamp> ts_cls(m, "EventTimestamp");
     ts_cls
