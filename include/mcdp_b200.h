@@ -28,8 +28,9 @@
 extern "C" {
 #endif
 
-#define MCDP_ABI_VERSION 3 /* 2: + mcdp_run_attribution_device / _host; 3: + mcdp_plan_launch_shape,
-                              MCDP_OPT_SAMPLES_PER_LANE (both additive) */
+#define MCDP_ABI_VERSION 4 /* 2: + mcdp_run_attribution_device / _host; 3: + mcdp_plan_launch_shape,
+                              MCDP_OPT_SAMPLES_PER_LANE (both additive); 4: + MCDP_OPT_CLUSTER_SIZE, mcdp_planset_*,
+                              launch_shape slot 6 reports the cluster size (generator contract mcdp-philox-v2) */
 
 enum {
     MCDP_OK = 0,
@@ -108,9 +109,12 @@ enum {
     MCDP_OPT_RNG_STREAM = 4,      /* 0 = Philox contract (default); 1 = reference-compatible stream: Xoshiro256++
                                      in activity-index order with the libstdc++ transforms (_core.cpp:313-329),
                                      full-output calls only, at most 64 distributions */
-    MCDP_OPT_SAMPLES_PER_LANE = 5 /* samples a lane owns in the sweep kernel: 2 = 64-sample groups at 64 registers,
-                                     4 = 128-sample groups at 128 registers with 256-bit row accesses (needs 32-byte
+    MCDP_OPT_SAMPLES_PER_LANE = 5, /* samples a lane owns in the sweep kernel: 2 = 64-sample groups at 64 registers,
+                                     4 = 128-sample groups at 96 registers with 256-bit row accesses (needs 32-byte
                                      aligned buffers, else falls back to 2); 0 = auto.  Results do not depend on it. */
+    MCDP_OPT_CLUSTER_SIZE = 6      /* quad kernel, launches with fewer sample groups than SMs: CTAs per thread-block
+                                     cluster that share one group and split its levels (2, 4, 8); 1 = never; 0 = auto.
+                                     Results do not depend on it. */
 };
 
 const char* mcdp_last_error(void);
@@ -147,8 +151,8 @@ int64_t mcdp_plan_get_chunks(const mcdp_plan* plan, int32_t rows, int32_t dense,
 
 /* The launch shape a call over n samples would take (introspection for tests, tooling and the benchmark's
  * kernel label; works on host-only plans, which assume 148 SMs).  out8 = {samples per lane (2 pair kernel, 4 quad
- * kernel), warps per group, groups per CTA, threads per CTA, grid size, dynamic shared memory bytes, 64-sample
- * batches folded per group (reduced mode), 1 if the tables are staged in shared memory}. */
+ * kernel), warps per group, groups per CTA, threads per CTA, grid size, dynamic shared memory bytes, CTAs per
+ * thread-block cluster (1 = no cluster launch), 1 if the tables are staged in shared memory}. */
 int32_t mcdp_plan_launch_shape(const mcdp_plan* plan, int64_t n, int32_t reduced, int32_t n_bins, int64_t* out8);
 
 /* ---- device-buffer entry points (asynchronous on `stream`, a cudaStream_t passed as void*) ----

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_PKG, "libmcdp_b200.so")
 MCDP_OK, MCDP_ERR_INVALID, MCDP_ERR_CUDA, MCDP_ERR_ARG = 0, 1, 2, 3
 DEVICE_NONE = -1
 OPT_STREAM_KEY, OPT_WARPS_PER_GROUP, OPT_GROUPS_PER_CTA, OPT_HOST_CHUNK, OPT_RNG_STREAM, OPT_SAMPLES_PER_LANE = 0, 1, 2, 3, 4, 5
+OPT_CLUSTER_SIZE = 6
 RNG_PHILOX, RNG_REFERENCE = 0, 1
 MAX_THRESHOLDS = 4
 CHUNK_UNITS = 16
@@ -212,8 +213,8 @@ class Plan:
         self.device = int(L.mcdp_plan_device(h))
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().mcdp_plan_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None:  # (_lib is None again at interpreter shutdown)
+            _lib.mcdp_plan_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -243,7 +244,7 @@ class Plan:
         """The launch a call over n samples would take (which kernel, CTA shape); works on host-only plans."""
         out = np.zeros(8, np.int64)
         _check(lib().mcdp_plan_launch_shape(self._h, int(n), int(bool(reduced)), int(n_bins), out.ctypes.data))
-        keys = ("samples_per_lane", "warps_per_group", "groups_per_cta", "threads", "grid", "smem_bytes", "batches", "smem_tables")
+        keys = ("samples_per_lane", "warps_per_group", "groups_per_cta", "threads", "grid", "smem_bytes", "cluster", "smem_tables")
         return dict(zip(keys, out.tolist()))
 
     def set_option(self, option: int, value: int) -> None:

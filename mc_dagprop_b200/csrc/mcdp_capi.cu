@@ -131,17 +131,9 @@ struct mcdp_plan {
         int32_t n_chunks = 0;
         bool ready = false;
     } streams[2][2];
-    DevBuf<unsigned char> d_stream_red;   // reduced mode, several batches per group: event + precedence records
-    std::vector<EventRec> ev_red;         // host copies of the slot-row records (built once)
+    std::vector<EventRec> ev_red;         // reduced modes: host copies of the slot-row records (built once)
     std::vector<PredRec> pr_red;
     size_t l2_persist_bytes = 0, l2_window_max = 0;
-    struct RecPtrs {
-        EventRec* p = nullptr;
-    } d_events_red;
-    struct PredPtrs {
-        PredRec* p = nullptr;
-    } d_preds_red;
-    DevBuf<int32_t> d_level_begin;
     DevBuf<PredRec> d_orphans;
     DevBuf<DistRec> d_dists;
     DevBuf<double> d_tab;
@@ -153,6 +145,7 @@ struct mcdp_plan {
     uint32_t stream_key = 0;
     int warps_per_group = 0, groups_per_cta = 0;
     int samples_per_lane = 0;  // 0 auto, 2 pair kernel (mcdp_chunk_sweep.cuh), 4 quad kernel (mcdp_quad_sweep.cuh)
+    int cluster_size = 0;      // 0 auto, 1 never, 2 / 4 / 8: CTAs per cluster that share one sample group (quad kernel)
     int64_t host_chunk = 0;
     int rng_stream = 0;  // 0 Philox contract, 1 reference-compatible Xoshiro stream
     DevBuf<ActRec> d_acts;
@@ -228,8 +221,6 @@ mcdp_plan::~mcdp_plan() {
                 st.units.release();
                 st.level_begin.release();
             }
-        d_stream_red.release();
-        d_level_begin.release();
         d_orphans.release();
         d_dists.release();
         d_tab.release();
@@ -252,24 +243,13 @@ int32_t upload(DevBuf<T>& buf, const std::vector<T>& v) {
     return MCDP_OK;
 }
 
-// events then precedence records, back to back in one allocation
-int32_t upload_stream(DevBuf<unsigned char>& pool, const std::vector<EventRec>& ev, const std::vector<PredRec>& pr,
-                      EventRec** d_ev, PredRec** d_pr) {
-    const size_t eb = ev.size() * sizeof(EventRec), pb = pr.size() * sizeof(PredRec);
-    MCDP_CUDA(pool.ensure(eb + pb));
-    *d_ev = reinterpret_cast<EventRec*>(pool.p);
-    *d_pr = reinterpret_cast<PredRec*>(pool.p + eb);
-    if (eb) MCDP_CUDA(cudaMemcpy(*d_ev, ev.data(), eb, cudaMemcpyHostToDevice));
-    if (pb) MCDP_CUDA(cudaMemcpy(*d_pr, pr.data(), pb, cudaMemcpyHostToDevice));
-    return MCDP_OK;
-}
-
 struct LaunchShape {
     int wpg, gpc, threads, batches;
     unsigned grid;
     size_t smem;
     bool smem_tables;
     int spl;  // samples per lane: 2 = pair kernel (64-sample groups), 4 = quad kernel (128-sample groups)
+    int cluster = 1;  // quad kernel, one group per CTA: CTAs per thread-block cluster splitting the group's levels
     // what the shape was chosen for (launch_sweep re-chooses with spl = 2 when the buffers are not 32-byte aligned)
     bool reduced, single_batch;
     int n_bins;
@@ -285,16 +265,7 @@ LaunchShape choose_shape_spl(const mcdp_plan* plan, int64_t n, bool reduced, int
     s.single_batch = single_batch;
     s.n_bins = n_bins;
     int64_t n_groups = (n + 63) / 64;
-    int batches = 1;
-    if (reduced && !single_batch) {
-        // once there are more 64-sample batches than warp slots, fold several batches per group so the
-        // global accumulators see one flush per event per group instead of one per 64 samples
-        const int64_t slots = int64_t(plan->sm_count) * 32;
-        batches = int(std::max<int64_t>(1, std::min<int64_t>(64, n_groups / slots)));
-        n_groups = (n_groups + batches - 1) / batches;
-    }
-    // the quad kernel covers everything but the multi-batch reduced launches (mcdp_sweep.cuh)
-    if (batches > 1) spl = 2;
+    const int batches = 1;  // every reduced launch is single-batch since the quad kernel stages its statistics
     s.spl = spl;
     const int sm_warps = spl == 4 ? MCDP_QUAD_MAX_THREADS / 32 : 32;  // resident warps per SM: 96 vs 64 registers per thread
     if (spl == 4) n_groups = (n + kQuadSamples - 1) / kQuadSamples;
@@ -339,17 +310,31 @@ LaunchShape choose_shape_spl(const mcdp_plan* plan, int64_t n, bool reduced, int
     s.batches = batches;
     s.threads = 32 * wpg * gpc;
     s.grid = unsigned((n_groups + gpc - 1) / gpc);
+    // Small launches of the quad kernel: fewer groups than SMs.  Spread each group over a thread-block cluster whose
+    // CTAs split the levels (mcdp_quad_sweep.cuh), as far as the levels can feed the warps (about one chunk per warp
+    // per level) and the machine has SMs to give.
+    s.cluster = 1;
+    if (spl == 4 && wpg > 1 && gpc == 1 && plan->cluster_size != 1 && n_groups > 0) {
+        int c = 1;
+        if (plan->cluster_size > 1) {
+            c = plan->cluster_size;
+        } else {
+            const int64_t chunks_per_level = h.n_levels > 0 ? int64_t(h.units.size() / size_t(kChunkUnits)) / h.n_levels : 0;
+            while (c < 8 && int64_t(2 * c) * n_groups <= plan->sm_count && int64_t(2 * c) * wpg <= chunks_per_level) c *= 2;
+        }
+        s.cluster = c;
+        s.grid *= unsigned(c);
+    }
     if (eff_out) {
         const int64_t per_sm = std::max(1, sm_warps / (wpg * gpc));
         const int64_t slots = int64_t(plan->sm_count) * per_sm;
         const int64_t waves = std::max<int64_t>(1, (int64_t(s.grid) + slots - 1) / slots);
-        *eff_out = double(n_groups * wpg) / double(waves * plan->sm_count * sm_warps);
+        *eff_out = double(n_groups * wpg * s.cluster) / double(waves * plan->sm_count * sm_warps);
     }
     const size_t need = sizeof(DistRec) * h.dists.size() + sizeof(double) * h.tab_pool.size();
     // keep several CTAs per SM resident: stage only when the tables are a modest share of shared memory
     s.smem_tables = need > 0 && need <= std::min<size_t>(plan->smem_optin, 64 * 1024);
     s.smem = size_t(kLogTabBytes) + (s.smem_tables ? need : 0);  // the log table of mcdp_math.cuh is always staged
-    if (reduced && n_bins > 0 && batches > 1) s.smem = ((s.smem + 15) & ~size_t(15)) + size_t(wpg * gpc) * size_t(n_bins) * 4;
     return s;
 }
 
@@ -387,19 +372,26 @@ int32_t launch_kernel(mcdp_plan* plan, K k, const SweepParams& p, const LaunchSh
     cfg.blockDim = dim3(unsigned(s.threads));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     unsigned n_attr = 0;
+    if (s.cluster > 1) {
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = unsigned(s.cluster);
+        attr[n_attr].val.clusterDim.y = 1;
+        attr[n_attr].val.clusterDim.z = 1;
+        ++n_attr;
+    }
     if (plan->l2_persist_bytes > 0 && plan->l2_window_max > 0 && stream_bytes > 0) {
         // the plan stream is re-read by every group while >100 GB of outputs stream through L2: pin it with a
         // persisting access-policy window
         const size_t win = std::min(stream_bytes, plan->l2_window_max);
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(stream_base);
-        attr[0].val.accessPolicyWindow.num_bytes = win;
-        attr[0].val.accessPolicyWindow.hitRatio = float(std::min(1.0, double(plan->l2_persist_bytes) / double(win)));
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        n_attr = 1;
+        attr[n_attr].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[n_attr].val.accessPolicyWindow.base_ptr = const_cast<void*>(stream_base);
+        attr[n_attr].val.accessPolicyWindow.num_bytes = win;
+        attr[n_attr].val.accessPolicyWindow.hitRatio = float(std::min(1.0, double(plan->l2_persist_bytes) / double(win)));
+        attr[n_attr].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[n_attr].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ++n_attr;
     }
     cfg.attrs = attr;
     cfg.numAttrs = n_attr;
@@ -412,8 +404,10 @@ int32_t ensure_chunk_stream(mcdp_plan* plan, bool reduced, bool dense, SweepPara
 // the launch-shape dependent fields of the parameter block
 void apply_shape(SweepParams& p, const LaunchShape& s) {
     p.smem_ring_off = uint32_t((s.smem + 127) & ~size_t(127));
+    p.smem_stat_off = p.smem_ring_off + uint32_t(chunk_ring_bytes(s.threads / 32));
     p.warps_per_group = s.wpg;
     p.batches_per_group = s.batches;
+    p.cluster_size = s.cluster;
 }
 
 bool aligned32(const void* a) { return (reinterpret_cast<uintptr_t>(a) & 31) == 0; }
@@ -428,20 +422,14 @@ int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p_in, const LaunchShape
         s = choose_shape(plan, p.n, s.reduced, s.n_bins, s.single_batch, 2);
         apply_shape(p, s);
     }
-    if constexpr (MODE == kModeReduced) {
-        // event + precedence record streams (mcdp_sweep.cuh)
-        const size_t bytes = size_t(plan->host.E) * sizeof(EventRec) + size_t(plan->host.P) * sizeof(PredRec);
-        if (s.batches > 1)
-            return s.smem_tables ? launch_kernel(plan, sweep_kernel<MODE, true, true>, p, s, s.smem, p.events, bytes, stream)
-                                 : launch_kernel(plan, sweep_kernel<MODE, false, true>, p, s, s.smem, p.events, bytes, stream);
-    }
     {
         // chunk stream (mcdp_chunk_sweep.cuh): tables (128-byte rounded) + per-warp chunk ring.  One warp per
         // group walks the dense stream, several warps per group split the level-aligned one.
         const int32_t rc = ensure_chunk_stream(plan, MODE == kModeReduced || MODE == kModeAttr, s.wpg == 1, p);
         if (rc) return rc;
         const size_t bytes = size_t(p.n_chunks) * size_t(kChunkBytes);
-        const size_t smem = ((s.smem + 127) & ~size_t(127)) + chunk_ring_bytes(s.threads / 32);
+        size_t smem = ((s.smem + 127) & ~size_t(127)) + chunk_ring_bytes(s.threads / 32);
+        if (s.spl == 4 && (MODE == kModeReduced || MODE == kModeAttr)) smem += quad_stat_bytes(s.threads / 32);
         if (s.spl == 4) {
             if (s.wpg > 1)
                 return s.smem_tables ? launch_kernel(plan, quad_sweep_kernel<MODE, true, true>, p, s, smem, p.chunks, bytes, stream)
@@ -460,7 +448,6 @@ int32_t launch_sweep(mcdp_plan* plan, const SweepParams& p_in, const LaunchShape
 SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, int64_t ld) {
     SweepParams p{};
     const HostPlan& h = plan->host;
-    p.level_begin = plan->d_level_begin.p;
     p.orphans = plan->d_orphans.p;
     p.dists = plan->d_dists.p;
     p.tab_pool = plan->d_tab.p;
@@ -475,7 +462,6 @@ SweepParams base_params(const mcdp_plan* plan, const LaunchShape& s, int64_t n, 
     p.n_dists = int32_t(h.dists.size());
     p.tab_pool_len = int32_t(h.tab_pool.size());
     p.E = h.E;
-    p.last_pred = h.P > 0 ? uint32_t(h.P - 1) : 0u;
     p.max_delay = h.max_delay;
     for (int r = 0; r < 10; ++r) p.keys.k[r] = plan->stream_key + uint32_t(r) * 0x9E3779B9u;
     apply_shape(p, s);
@@ -515,8 +501,6 @@ int32_t ensure_reduced_stream(mcdp_plan* plan) {
         for (uint32_t k = 0; k < e.fan_in; ++k)
             pr[e.pred_begin + k].next_src_row = k + 1 < e.fan_in ? pr[e.pred_begin + k + 1].src_row : 0u;
     }
-    int32_t rc = upload_stream(plan->d_stream_red, ev, pr, &plan->d_events_red.p, &plan->d_preds_red.p);
-    if (rc) return rc;
     plan->red_ready = true;
     return MCDP_OK;
 }
@@ -660,8 +644,7 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
     }
     const HostPlan& h = plan->host;
     NvtxRange nvtx_upload("mcdp:plan H2D");
-    int32_t rc = upload(plan->d_level_begin, h.level_begin);
-    if (!rc) rc = upload(plan->d_orphans, h.orphans);
+    int32_t rc = upload(plan->d_orphans, h.orphans);
     if (!rc) rc = upload(plan->d_dists, h.dists);
     if (!rc) rc = upload(plan->d_tab, h.tab_pool);
     if (!rc) {
@@ -701,6 +684,11 @@ int32_t mcdp_plan_set_option(mcdp_plan* plan, int32_t option, int64_t value) {
         case MCDP_OPT_SAMPLES_PER_LANE:
             if (value != 0 && value != 2 && value != 4) return fail(MCDP_ERR_ARG, "samples per lane must be 0 (auto), 2 or 4");
             plan->samples_per_lane = int(value);
+            break;
+        case MCDP_OPT_CLUSTER_SIZE:
+            if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8)
+                return fail(MCDP_ERR_ARG, "cluster size must be 0 (auto), 1, 2, 4 or 8");
+            plan->cluster_size = int(value);
             break;
         case MCDP_OPT_HOST_CHUNK:
             if (value < 0) return fail(MCDP_ERR_ARG, "host chunk must be non-negative");
@@ -768,8 +756,9 @@ int32_t mcdp_plan_launch_shape(const mcdp_plan* plan, int64_t n, int32_t reduced
     out8[2] = s.gpc;
     out8[3] = s.threads;
     out8[4] = int64_t(s.grid);
-    out8[5] = int64_t(s.batches > 1 ? s.smem : ((s.smem + 127) & ~size_t(127)) + chunk_ring_bytes(s.threads / 32));
-    out8[6] = s.batches;
+    out8[5] = int64_t(((s.smem + 127) & ~size_t(127)) + chunk_ring_bytes(s.threads / 32) +
+                      (s.spl == 4 && reduced ? quad_stat_bytes(s.threads / 32) : 0));
+    out8[6] = s.cluster;
     out8[7] = s.smem_tables ? 1 : 0;
     return MCDP_OK;
 }
@@ -866,8 +855,6 @@ int32_t run_attribution_locked(mcdp_plan* plan, const int32_t* d_seeds, int32_t 
         SweepParams p = base_params(plan, s, m, chunk);
         p.cause_act = d_cause_act;
         p.cause_none = d_cause_none;
-        p.events = plan->d_events_red.p;
-        p.preds = plan->d_preds_red.p;
         p.seeds = d_seeds ? d_seeds + off : nullptr;
         p.seed0 = int32_t(uint32_t(seed0) + uint32_t(off));
         p.realized = plan->d_scratch.p;

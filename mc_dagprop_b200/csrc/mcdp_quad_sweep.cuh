@@ -40,6 +40,37 @@ __device__ __forceinline__ void stcs_d4(void* ptr, const D4& v) {
 
 constexpr int kQuadSamples = 128;  // samples per group
 
+// Reduced modes: per-warp staging of the per-event statistics in shared memory (behind the chunk rings).  A warp parks
+// the per-lane partial sums of up to kStatSlots events (and their histogram counts, as 16-bit pairs) and folds them
+// in one transposed pass -- lane -> (event, lane block) -- instead of running a five-stage shuffle butterfly and four
+// match.any rounds per event.  Layout per warp: [kStatSlots][32] {sum, sum of squares} f64 pairs, then
+// [kStatSlots][32] u32 histogram words (two bins per word, so up to kStatMaxBins bins).
+constexpr int kStatSlots = 4;
+constexpr int kStatMaxBins = 64;
+constexpr int kStatSumBytes = kStatSlots * 32 * 16;
+constexpr int kStatHistBytes = kStatSlots * 32 * 4;
+constexpr int kStatStride = kStatSumBytes + kStatHistBytes;
+__host__ __device__ inline size_t quad_stat_bytes(int n_warps) { return size_t(n_warps) * size_t(kStatStride); }
+
+// c += K when x > th: one compare and one predicated add (the C form costs a select and an add per term)
+__device__ __forceinline__ void add_if_gt(uint32_t& c, double x, double th, uint32_t k) {
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}" : "+r"(c) : "d"(x), "d"(th), "r"(k));
+}
+// Thread-block cluster (small launches): the CTAs of a cluster share ONE sample group and split every level between
+// them, so a launch with fewer groups than SMs still spreads over the machine.  Rows written by one CTA are read by
+// the others through L2 (st.cg / ld.cg); the per-level cluster barrier orders them (release / acquire).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void atoms_add_u32(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // CTA size limit of the quad kernel: 640 threads = 20 resident warps per SM at 96 registers.  Measured on B200
 // (C3, profiles/r01_quad_ab.txt): 16 warps at 128 registers 77 % of the measured HBM peak, 20 warps at 96
 // registers 80.5 %, 24 warps at 80 registers 62 % (spills).
@@ -92,14 +123,25 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
         mbar_init(bar0 + 8, 1);
         mbar_fence_init();
     }
+    // reduced modes: this warp's statistics staging area; the histogram words start at zero
+    const uint32_t stat0 = smem_base + p.smem_stat_off + uint32_t(warp) * uint32_t(kStatStride);
+    const bool stage_hist = kReduced && p.hist != nullptr && p.n_bins <= kStatMaxBins;
+    if constexpr (kReduced) {
+#pragma unroll
+        for (int k = 0; k < kStatSlots; ++k)
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(stat0 + uint32_t(kStatSumBytes) + uint32_t(k * 32 + lane) * 4u), "r"(0u) : "memory");
+    }
     __syncthreads();
 
     const int wpg = DYN ? p.warps_per_group : 1;
     const int group_in_cta = warp / wpg;
     const int wsub = warp - group_in_cta * wpg;
     const int groups_per_cta = n_warps / wpg;
-    const int64_t batch0 = int64_t(blockIdx.x) * groups_per_cta + group_in_cta;
-    if (batch0 * kQuadSamples >= p.n) return;  // whole group (all its warps) out of range
+    // cluster launch (DYN, one group per CTA): the group is the cluster, this CTA takes every csize-th chunk of a level
+    const int csize = DYN ? p.cluster_size : 1;
+    const int crank = (DYN && csize > 1) ? int(cluster_ctarank()) : 0;
+    const int64_t batch0 = csize > 1 ? int64_t(blockIdx.x) / csize : int64_t(blockIdx.x) * groups_per_cta + group_in_cta;
+    if (batch0 * kQuadSamples >= p.n) return;  // whole group (all its warps, all CTAs of its cluster) out of range
     const PhiloxKeys& key0 = p.keys;
 
     // The lane's four sample columns.  ld is a multiple of 64, not necessarily of 128: in the last group the
@@ -124,6 +166,7 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
         }
     }
     sd.quad = ((sd.s[0] & 1u) == 0u) && sd.s[1] == sd.s[0] + 1u && sd.s[2] == sd.s[0] + 2u && sd.s[3] == sd.s[0] + 3u;
+    sd.quad4 = sd.quad && (sd.s[0] & 3u) == 0u;
     const uint32_t lane_off = uint32_t(s0) * 8u;
     uint64_t lane_off64 = lane_off;  // kept as a register pair: the 64-bit addend of the row multiply-add
     asm volatile("" : "+l"(lane_off64));
@@ -150,20 +193,20 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
         }
     };
 
-    // ---- level cursor (DYN) ----
+    // ---- level cursor (DYN): counts the chunks this CTA has taken in the current level; chunk = lb + k * csize + crank ----
     __shared__ int s_cursor[16][2];
     if constexpr (DYN) {
         if (wsub == 0 && lane == 0) s_cursor[group_in_cta][0] = 0;
         group_barrier(1 + group_in_cta, wpg * 32);
     }
-    int seq = 0;
+    int seq = 0, lb = 0;
     auto grab = [&](int parity) -> int {
         if constexpr (!DYN) {
             return seq++;
         } else {
             int v = 0;
             if (lane == 0) v = atomicAdd(&s_cursor[group_in_cta][parity], 1);
-            return __shfl_sync(0xFFFFFFFFu, v, 0);
+            return lb + __shfl_sync(0xFFFFFFFFu, v, 0) * csize + crank;
         }
     };
 
@@ -178,6 +221,56 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
     bool valid[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) valid[i] = !shadow && s0 + i < p.n;
+    // ---- reduced modes: statistics staged per warp, folded every kStatSlots events ----
+    int n_staged = 0;      // events parked in the staging area (warp-uniform)
+    uint32_t my_ev = 0u;   // lane k < n_staged: event id of slot k
+    const bool all_valid = valid[0] && valid[1] && valid[2] && valid[3];
+    auto flush_stats = [&]() {
+        __syncwarp();
+        // Sums: lane -> (slot e = lane & 3, lane block = lane >> 2): four parked {sum, sumsq} pairs each, then three
+        // shuffle stages over the eight blocks.  The element order inside a block is rotated by e so that the eight
+        // lanes of a quarter warp read eight different 16-byte bank groups.
+        const int e = lane & 3, blk = lane >> 2;
+        double as = 0.0, aq = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double a, b;
+            asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];"
+                         : "=d"(a), "=d"(b)
+                         : "r"(stat0 + uint32_t(e * 32 + blk * 4 + ((k + e) & 3)) * 16u));
+            as += a;
+            aq += b;
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            as += __shfl_xor_sync(0xFFFFFFFFu, as, o);
+            aq += __shfl_xor_sync(0xFFFFFFFFu, aq, o);
+        }
+        if (lane < n_staged) {  // lane == e here: its own slot's event
+            if (p.sum) atomicAdd(p.sum + my_ev, as);
+            if (p.sumsq) atomicAdd(p.sumsq + my_ev, aq);
+        }
+        if (stage_hist) {
+            const int nb = p.n_bins;
+#pragma unroll
+            for (int k = 0; k < kStatSlots; ++k) {
+                const uint32_t evk = __shfl_sync(0xFFFFFFFFu, my_ev, k);
+                if (k < n_staged) {
+                    const uint32_t wa = stat0 + uint32_t(kStatSumBytes) + uint32_t(k * 32 + lane) * 4u;
+                    uint32_t w;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(wa));
+                    if (w) {
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(0u) : "memory");
+                        uint32_t* h = p.hist + size_t(evk) * nb + 2 * lane;
+                        if (w & 0xFFFFu) atomicAdd(h, w & 0xFFFFu);
+                        if (w >> 16) atomicAdd(h + 1, w >> 16);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        n_staged = 0;
+    };
     auto finalize = [&]() {
         // _core.cpp:348-349
         double r[4];
@@ -195,32 +288,55 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
             double x[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) x[i] = valid[i] ? r[i] - ev_earliest : 0.0;
-            uint32_t late_packed = 0u;
+            // sum and sum of squares of this lane's samples: parked, folded across lanes in flush_stats
+            {
+                const double sl = (x[0] + x[1]) + (x[2] + x[3]);
+                const double ql = (x[0] * x[0] + x[1] * x[1]) + (x[2] * x[2] + x[3] * x[3]);
+                asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(stat0 + uint32_t(n_staged * 32 + lane) * 16u), "d"(sl), "d"(ql)
+                             : "memory");
+            }
             if (p.late) {
+                // exceedance counts, 8 bits per threshold (at most 128 samples per warp): one REDUX, the atomics of the
+                // thresholds issued by different lanes of one instruction
+                uint32_t late_packed = 0u;
 #pragma unroll
                 for (int t = 0; t < MCDP_MAX_THRESHOLDS; ++t) {
                     if (t < p.n_thresholds) {
                         const double th = p.thresholds[t];
-                        uint32_t c = 0u;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) c += uint32_t(valid[i] && x[i] > th);
-                        late_packed |= c << (8 * t);
+                        for (int i = 0; i < 4; ++i)
+                            if (all_valid || valid[i]) add_if_gt(late_packed, x[i], th, 1u << (8 * t));
+                    }
+                }
+                const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, late_packed);
+                if (lane < p.n_thresholds) {
+                    const uint32_t cnt = (tot >> (8 * lane)) & 0xFFu;
+                    if (cnt) atomicAdd(p.late + size_t(lane) * p.E + ev, (unsigned long long)cnt);
+                }
+            }
+            if (p.hist) {
+                const int nb = p.n_bins;
+                int b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) b[i] = min(max(int(floor((x[i] - p.hist_lo) * p.hist_scale)), 0), nb - 1);
+                if (stage_hist) {
+                    // counts into this warp's private 16-bit-pair histogram of the slot (shared-memory reductions)
+                    const uint32_t h0 = stat0 + uint32_t(kStatSumBytes) + uint32_t(n_staged) * 128u;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (all_valid || valid[i]) atoms_add_u32(h0 + uint32_t(b[i] >> 1) * 4u, 1u << ((b[i] & 1) * 16));
+                } else {
+                    uint32_t* h = p.hist + size_t(ev) * nb;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int key = valid[i] ? b[i] : -1 - lane;  // unique keys: match groups of size 1, skipped below
+                        const unsigned g = __match_any_sync(0xFFFFFFFFu, key);
+                        if (key >= 0 && lane == __ffs(g) - 1) atomicAdd(h + key, uint32_t(__popc(g)));
                     }
                 }
             }
-            flush_sums(p, ev, lane, (x[0] + x[1]) + (x[2] + x[3]), (x[0] * x[0] + x[1] * x[1]) + (x[2] * x[2] + x[3] * x[3]),
-                       late_packed);
-            if (p.hist) {
-                const int nb = p.n_bins;
-                uint32_t* h = p.hist + size_t(ev) * nb;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    int b = min(max(int(floor((x[i] - p.hist_lo) * p.hist_scale)), 0), nb - 1);
-                    if (!valid[i]) b = -1 - lane;  // unique keys: match groups of size 1, skipped below
-                    const unsigned g = __match_any_sync(0xFFFFFFFFu, b);
-                    if (b >= 0 && lane == __ffs(g) - 1) atomicAdd(h + b, uint32_t(__popc(g)));
-                }
-            }
+            if (lane == n_staged) my_ev = ev;
+            if (++n_staged == kStatSlots) flush_stats();
             if constexpr (MODE == kModeAttr) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -315,7 +431,7 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
         const int le = DYN ? __ldg(p.chunk_level_begin + lvl + 1) : p.n_chunks;
         const int par = lvl & 1;
         if constexpr (DYN) {
-            if (wsub == 0 && lane == 0) s_cursor[group_in_cta][par ^ 1] = le;
+            if (wsub == 0 && lane == 0) s_cursor[group_in_cta][par ^ 1] = 0;  // re-armed for the next level
         }
         int c = grab(par);
         bool from_cursor = true;
@@ -352,12 +468,19 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
             __syncwarp();
             c = cn;
         }
-        if constexpr (DYN) group_barrier(1 + group_in_cta, wpg * 32);
+        if constexpr (DYN) {
+            lb = le;
+            if (csize > 1) cluster_barrier();
+            else group_barrier(1 + group_in_cta, wpg * 32);
+        }
+    }
+    if constexpr (kReduced) {
+        if (n_staged) flush_stats();
     }
 
     if constexpr (MODE == kModeFull) {
         // activities no precedence entry references still get their sampled duration (_core.cpp:323-329)
-        for (int i = wsub; i < p.n_orphans; i += wpg) {
+        for (int i = wsub + crank * wpg; i < p.n_orphans; i += wpg * csize) {
             const int4 q0 = __ldg(reinterpret_cast<const int4*>(p.orphans + i));
             const int4 q1 = __ldg(reinterpret_cast<const int4*>(p.orphans + i) + 1);
             const uint32_t act = uint32_t(q0.y), meta = uint32_t(q1.x);

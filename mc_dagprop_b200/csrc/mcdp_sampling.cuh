@@ -1,4 +1,4 @@
-// mcdp_sampling.cuh -- device generator "mcdp-philox-v1" (DESIGN.md section 4).
+// mcdp_sampling.cuh -- device generator "mcdp-philox-v2" (DESIGN.md section 4).
 //
 // Replaces the reference's sequential Xoshiro256++ stream (_custom_rng.hpp:551-600) and the
 // libstdc++ <random> transforms behind Dist::sample (_core.cpp:72-141) by counter-based draws
@@ -7,8 +7,17 @@
 // activities can be drawn in evaluation order, fused with the max-plus sweep.
 //
 //   key     = (stream_key, 'MCDP')                     -- round keys precomputed, read as constant operands
-//   PAIR    ctr = (seed >> 1, act, j, 'PAIR')          -- one block serves seeds {2k, 2k+1}: 64 bits each
-//   SOLO    ctr = (seed,      act, t, 'SOLO')          -- gamma attempt t: 4 x 32 bits
+//   QUAD    ctr = (seed >> 2, act, j, 'QUAD')          -- one block serves seeds {4k .. 4k+3}: 32 bits each (word seed & 3):
+//                                                         empirical tables of <= 4096 entries, exponentials with
+//                                                         max_scale <= 16 lambda, gamma shape 1
+//   PAIR    ctr = (seed >> 1, act, j, 'PAIR')          -- one block serves seeds {2k, 2k+1}: 64 bits each (the other
+//                                                         tables and exponentials)
+//   SOLO    ctr = (seed,      act, t, 'SOLO')          -- gamma attempt t >= 1: 4 x 32 bits
+//   GAM0    ctr = (seed >> 1, act, 0, 'GAM0')          -- gamma attempt 0 of the seed pair: one Box-Muller pair
+//                                                         (cos branch: even seed, sin branch: odd seed) + two accept words
+//   GBST    ctr = (seed >> 2, act, 0, 'GBST')          -- shape < 1 boost uniform of attempt 0, word seed & 3
+// v1 (round 1) spent a 64-bit PAIR draw on every table lookup and exponential: two Philox blocks per lane-quad where
+// one suffices, 26 % of all instructions of the headline workload were Philox rounds.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -22,6 +31,9 @@ namespace mcdp {
 constexpr uint32_t kKey1 = 0x4D434450u;     // 'MCDP'
 constexpr uint32_t kTagPair = 0x50414952u;  // 'PAIR'
 constexpr uint32_t kTagSolo = 0x534F4C4Fu;  // 'SOLO'
+constexpr uint32_t kTagQuad = 0x51554144u;  // 'QUAD'
+constexpr uint32_t kTagGam0 = 0x47414D30u;  // 'GAM0'
+constexpr uint32_t kTagGbst = 0x47425354u;  // 'GBST'
 constexpr uint32_t kGammaMaxAttempts = 65536u;
 
 struct Philox4 {
@@ -71,6 +83,23 @@ __device__ __forceinline__ double uniform52(uint32_t lo, uint32_t hi) {
 // (w + 0.5) * 2^-32 in (0,1), exact.
 __device__ __forceinline__ double uniform32(uint32_t w) {
     return __hiloint2double(0x41300000, static_cast<int>(w)) - (1048576.0 - 0x1p-33);
+}
+
+__device__ __forceinline__ uint32_t philox_word(const Philox4& r, uint32_t k) {
+    return k == 0u ? r.x : (k == 1u ? r.y : (k == 2u ? r.z : r.w));
+}
+
+// one 32-bit draw for each of the two samples of a pair-kernel lane (QUAD-style blocks with tag `tag`)
+__device__ __forceinline__ void draw32x2(uint32_t seed_a, uint32_t seed_b, uint32_t ja, uint32_t jb, uint32_t act, uint32_t tag,
+                                         const PhiloxKeys& key0, uint32_t& wa, uint32_t& wb) {
+    if ((seed_a >> 2) == (seed_b >> 2) && ja == jb) {
+        const Philox4 r = philox4x32_10(seed_a >> 2, act, ja, tag, key0);
+        wa = philox_word(r, seed_a & 3u);
+        wb = philox_word(r, seed_b & 3u);
+    } else {
+        wa = philox_word(philox4x32_10(seed_a >> 2, act, ja, tag, key0), seed_a & 3u);
+        wb = philox_word(philox4x32_10(seed_b >> 2, act, jb, tag, key0), seed_b & 3u);
+    }
 }
 
 // Table / distribution-record access.  SMEM: the staged copy in shared memory, addressed by 32-bit
@@ -140,27 +169,39 @@ __device__ __forceinline__ float uniform23(uint32_t w) {
     return __uint_as_float(0x3F800000u | (w >> 9)) - (1.0f - 0x1p-24f);
 }
 
-// One Marsaglia-Tsang attempt (libstdc++ random.tcc:2352-2393 restated for SIMT): attempt t of
-// (seed, act) owns one SOLO Philox block.  The normal deviate (Box-Muller) and the two
-// accept/reject comparisons are evaluated with fp32 hardware approximations -- they only steer
-// the draw -- while the variate itself, x = d * v^3 * scale, is formed in fp64.  Returns true
-// when the attempt is accepted and x <= max_scale (the reference's outer `while (x > max_scale)`
-// loop, _core.cpp:98-104, simply continues the attempt sequence).
-struct GammaHalf {  // the fp32-steered part of one attempt, split so that two attempts can run in lockstep
+// One Marsaglia-Tsang attempt (libstdc++ random.tcc:2352-2393 restated for SIMT).  The normal deviate (Box-Muller)
+// and the two accept/reject comparisons are evaluated with fp32 hardware approximations -- they only steer the
+// draw -- while the variate itself, x = d * v^3 * scale, is formed in fp64.  An attempt is accepted when the
+// Marsaglia-Tsang test passes and x <= max_scale (the reference's outer `while (x > max_scale)` loop,
+// _core.cpp:98-104, simply continues the attempt sequence).
+//   attempt 0: the GAM0 block of the seed pair carries ONE Box-Muller pair (radius word, angle word) and one accept
+//              word per seed: the even seed takes r cos(a), the odd seed r sin(a) -- two independent normals for
+//              the price of one block; the shape < 1 boost uniform of attempt 0 is the seed's GBST word;
+//   attempt t >= 1: the SOLO block of (seed, act, t): radius, angle (cos branch), accept word, boost word.
+struct GammaHalf {  // the fp32-steered part of one attempt, split so that several attempts can run in lockstep
     float nf, n2, u;
     double v;
     bool pos, ok;
 };
+__device__ __forceinline__ float sin_approx(float x) {
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// Box-Muller radius and angle of a (radius word, angle word) pair
+__device__ __forceinline__ void box_muller_polar(uint32_t w_radius, uint32_t w_angle, float& r, float& ang) {
+    const float r2 = -1.3862943611198906f * lg2_approx(uniform23(w_radius));  // -2 ln u1
+    ang = float(int(w_angle)) * 1.4629180792671596e-9f;                        // 2 pi * int32 / 2^32, [-pi, pi)
+    r = sqrt_approx(fmaxf(r2, 0.0f));
+}
 template <bool SMEM>
-__device__ __forceinline__ void gamma_front(const DistView<SMEM>& d, const Philox4& w, GammaHalf& h) {
-    const float r2 = -1.3862943611198906f * lg2_approx(uniform23(w.x));  // -2 ln u1
-    const float ang = float(int(w.y)) * 1.4629180792671596e-9f;           // 2 pi * int32 / 2^32, [-pi, pi)
-    h.nf = sqrt_approx(fmaxf(r2, 0.0f)) * cos_approx(ang);
-    double v = fma(d.p(4), double(h.nf), 1.0);
+__device__ __forceinline__ void gamma_front(const DistView<SMEM>& d, float nf, uint32_t w_accept, GammaHalf& h) {
+    h.nf = nf;
+    double v = fma(d.p(4), double(nf), 1.0);
     h.pos = v > 0.0;
     h.v = v * v * v;
-    h.u = uniform23(w.z);
-    h.n2 = h.nf * h.nf;
+    h.u = uniform23(w_accept);
+    h.n2 = nf * nf;
     h.ok = h.u <= fmaf(-0.0331f * h.n2, h.n2, 1.0f);
 }
 template <bool SMEM>
@@ -171,68 +212,99 @@ __device__ __forceinline__ void gamma_exact(const DistView<SMEM>& d, GammaHalf& 
            fmaf(0.5f, h.n2, float(d.p(3)) * (1.0f - vf + 0.6931471805599453f * lg2_approx(vf)));
 }
 template <bool SMEM>
-__device__ __forceinline__ bool gamma_back(const DistView<SMEM>& d, const Philox4& w, const GammaHalf& h, double& x) {
+__device__ __forceinline__ bool gamma_back(const DistView<SMEM>& d, uint32_t w_boost, const GammaHalf& h, double& x) {
     x = d.p(6) * h.v;  // d * scale * v^3
-    if (d.flags() & 1) x *= double(ex2_approx(lg2_approx(uniform23(w.w)) * float(d.p(5))));  // u^(1/shape), shape < 1
+    if (d.flags() & 1) x *= double(ex2_approx(lg2_approx(uniform23(w_boost)) * float(d.p(5))));  // u^(1/shape), shape < 1
     return h.pos && h.ok && x <= d.p(2);
 }
+// attempt t >= 1 of one sample
 template <bool SMEM>
 __device__ __forceinline__ bool gamma_eval(const DistView<SMEM>& d, const Philox4& w, double& x) {
     GammaHalf h;
-    gamma_front<SMEM>(d, w, h);
+    float r, ang;
+    box_muller_polar(w.x, w.y, r, ang);
+    gamma_front<SMEM>(d, r * cos_approx(ang), w.z, h);
     if (!h.ok) gamma_exact<SMEM>(d, h);
-    return gamma_back<SMEM>(d, w, h, x);
+    return gamma_back<SMEM>(d, w.w, h, x);
 }
-// two attempts at once: one shared branch for the exact test, everything else straight-line
-template <bool SMEM>
-__device__ __forceinline__ void gamma_eval2(const DistView<SMEM>& d, const Philox4& wa, const Philox4& wb, double& xa,
-                                            double& xb, bool& ok_a, bool& ok_b) {
-    GammaHalf ha, hb;
-    gamma_front<SMEM>(d, wa, ha);
-    gamma_front<SMEM>(d, wb, hb);
-    if (!(ha.ok && hb.ok)) {
-        const bool sa = ha.ok, sb = hb.ok;
-        gamma_exact<SMEM>(d, ha);
-        gamma_exact<SMEM>(d, hb);
-        ha.ok = ha.ok || sa;  // a passed squeeze test stays accepted
-        hb.ok = hb.ok || sb;
+// The first attempts (t = 0) of N samples in lockstep: nf[i] / w_accept[i] / w_boost[i] prepared by the caller from the
+// GAM0 / GBST blocks.  One shared branch for the exact test, everything else straight-line.
+template <bool SMEM, int N>
+__device__ __forceinline__ void gamma_first_attempts(const DistView<SMEM>& d, const float (&nf)[N], const uint32_t (&w_accept)[N],
+                                                     const uint32_t (&w_boost)[N], double (&x)[N], bool (&ok)[N]) {
+    GammaHalf h[N];
+    bool all = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        gamma_front<SMEM>(d, nf[i], w_accept[i], h[i]);
+        all = all && h[i].ok;
     }
-    ok_a = gamma_back<SMEM>(d, wa, ha, xa);
-    ok_b = gamma_back<SMEM>(d, wb, hb, xb);
+    if (!all) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const bool squeeze = h[i].ok;  // a passed squeeze test stays accepted
+            gamma_exact<SMEM>(d, h[i]);
+            h[i].ok = h[i].ok || squeeze;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) ok[i] = gamma_back<SMEM>(d, w_boost[i], h[i], x[i]);
+}
+// the normal of `seed`'s attempt 0 out of its pair's GAM0 block, and its accept word
+__device__ __forceinline__ void gam0_take(const Philox4& blk, uint32_t seed, float& nf, uint32_t& w_accept) {
+    float r, ang;
+    box_muller_polar(blk.x, blk.y, r, ang);
+    const bool odd = seed & 1u;
+    nf = r * (odd ? sin_approx(ang) : cos_approx(ang));
+    w_accept = odd ? blk.w : blk.z;
 }
 
 // Gamma variates for the two samples of a thread.  First attempts run straight-line for both
 // samples; afterwards the whole warp iterates a uniform retry loop in which every lane retries one
 // pending sample, so a rejection costs the warp one extra attempt instead of one per sample.
 template <bool SMEM>
-__device__ __forceinline__ void gamma_variate2(const DistView<SMEM>& d, uint32_t seed_a, uint32_t seed_b, uint32_t act,
-                                               const PhiloxKeys& key0, double& xa, double& xb) {
-    // both first-attempt blocks are generated back to back: two independent multiply chains in flight
-    const Philox4 wa = philox4x32_10(seed_a, act, 0u, kTagSolo, key0);
-    const Philox4 wb = philox4x32_10(seed_b, act, 0u, kTagSolo, key0);
-    bool need_a, need_b;
-    gamma_eval2<SMEM>(d, wa, wb, xa, xb, need_a, need_b);
-    need_a = !need_a;
-    need_b = !need_b;
+__device__ __forceinline__ void gamma_variate2(const DistView<SMEM>& d, uint32_t seed_a, uint32_t seed_b, bool paired,
+                                               uint32_t act, const PhiloxKeys& key0, double& xa, double& xb) {
+    float nf[2];
+    uint32_t wacc[2], wboost[2] = {0u, 0u};
+    if (paired) {  // seeds {2k, 2k+1}: one GAM0 block, cos branch / sin branch
+        const Philox4 blk = philox4x32_10(seed_a >> 1, act, 0u, kTagGam0, key0);
+        float r, ang;
+        box_muller_polar(blk.x, blk.y, r, ang);
+        nf[0] = r * cos_approx(ang);
+        nf[1] = r * sin_approx(ang);
+        wacc[0] = blk.z;
+        wacc[1] = blk.w;
+    } else {
+        gam0_take(philox4x32_10(seed_a >> 1, act, 0u, kTagGam0, key0), seed_a, nf[0], wacc[0]);
+        gam0_take(philox4x32_10(seed_b >> 1, act, 0u, kTagGam0, key0), seed_b, nf[1], wacc[1]);
+    }
+    if (d.flags() & 1) draw32x2(seed_a, seed_b, 0u, 0u, act, kTagGbst, key0, wboost[0], wboost[1]);
+    double x[2];
+    bool ok[2];
+    gamma_first_attempts<SMEM, 2>(d, nf, wacc, wboost, x, ok);
+    xa = x[0];
+    xb = x[1];
+    bool need_a = !ok[0], need_b = !ok[1];
     uint32_t ta = 1u, tb = 1u;
     while (__any_sync(0xFFFFFFFFu, need_a || need_b)) {
         const bool do_a = need_a;
         const uint32_t seed = do_a ? seed_a : seed_b;
         const uint32_t t = do_a ? ta : tb;
-        double x;
-        const bool ok = gamma_eval<SMEM>(d, philox4x32_10(seed, act, t, kTagSolo, key0), x);
+        double xx;
+        const bool acc = gamma_eval<SMEM>(d, philox4x32_10(seed, act, t, kTagSolo, key0), xx);
         const bool give_up = t + 1u >= kGammaMaxAttempts;  // the reference would spin forever: clamp
-        if (give_up) x = fmin(x, d.p(2));
+        if (give_up) xx = fmin(xx, d.p(2));
         if (do_a) {
             ++ta;
-            if (ok || give_up) {
-                xa = x;
+            if (acc || give_up) {
+                xa = xx;
                 need_a = false;
             }
         } else if (need_b) {
             ++tb;
-            if (ok || give_up) {
-                xb = x;
+            if (acc || give_up) {
+                xb = xx;
                 need_b = false;
             }
         }
@@ -243,9 +315,9 @@ __device__ __forceinline__ void gamma_variate2(const DistView<SMEM>& d, uint32_t
 //   Gamma(k + h/2, scale) = scale * ( -ln(u_1 ... u_k)  +  h * (-ln u') cos^2(2 pi u'') ),   k = floor(shape), h in {0,1}
 // (a sum of k unit exponentials plus, for half-integer shapes, half the square of a Box-Muller
 // normal).  The logs are fp64 (log_pos), cos is the fp32 hardware approximation.  Up to two 32-bit
-// uniforms per sample come from a PAIR-style block shared by the seed pair, three or four from a
-// block per seed; draw j + 1 is used when x > max_scale (the reference's outer redraw loop,
-// _core.cpp:98-104).
+// uniforms per sample come from a PAIR-style block shared by the seed pair (one: from a QUAD-style block shared by
+// four seeds), three or four from a block per seed; draw j + 1 is used when x > max_scale (the reference's outer
+// redraw loop, _core.cpp:98-104).
 constexpr uint32_t kTagErlang = 0x45524C47u;  // 'ERLG'
 
 __device__ __forceinline__ double half_term(uint32_t wu, uint32_t wa, uint32_t log_tab) {
@@ -275,7 +347,12 @@ template <bool SMEM>
 __device__ __forceinline__ void erlang_draw2(const DistView<SMEM>& d, int variant, uint32_t seed_a, uint32_t seed_b, bool paired,
                                              uint32_t act, uint32_t ja, uint32_t jb, const PhiloxKeys& key0,
                                              uint32_t log_tab, double& ya, double& yb) {
-    if (variant <= 2 || variant == 4) {  // <= 64 bits per sample
+    if (variant == 2) {  // one 32-bit uniform per sample: QUAD-style block
+        uint32_t wa, wb;
+        draw32x2(seed_a, seed_b, ja, jb, act, kTagErlang, key0, wa, wb);
+        ya = erlang_value<SMEM>(d, variant, wa, 0u, 0u, 0u, log_tab);
+        yb = erlang_value<SMEM>(d, variant, wb, 0u, 0u, 0u, log_tab);
+    } else if (variant == 1 || variant == 4) {  // 64 bits per sample: PAIR-style block
         if (paired && ja == jb) {
             const Philox4 r = philox4x32_10(seed_a >> 1, act, ja, kTagErlang, key0);
             ya = erlang_value<SMEM>(d, variant, r.x, r.y, 0u, 0u, log_tab);
@@ -346,29 +423,47 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, t
         if (d.flags() & 8)
             erlang_variate2<SMEM>(d, seed_a, seed_b, paired, act, key0, log_tab, xa, xb);
         else
-            gamma_variate2<SMEM>(d, seed_a, seed_b, act, key0, xa, xb);
+            gamma_variate2<SMEM>(d, seed_a, seed_b, paired, act, key0, xa, xb);
         ea = __dmul_rn(xa, base);
         eb = __dmul_rn(xb, base);
         return;
     }
-    // one 64-bit draw per sample
-    uint32_t lo_a, hi_a, lo_b, hi_b;
-    if (paired) {  // seeds {2k, 2k+1}: one block, words 0-1 / 2-3
-        const Philox4 r = philox4x32_10(seed_a >> 1, act, 0u, kTagPair, key0);
-        lo_a = r.x;
-        hi_a = r.y;
-        lo_b = r.z;
-        hi_b = r.w;
+    // One uniform per sample.  Width by the contract's rule: 32 bits from a QUAD block for tables of <= 4096 entries and
+    // exponentials with max_scale <= 16 lambda (flags bit4), else 64 bits from a PAIR block.
+    const bool table = kind != MCDP_DIST_EXPONENTIAL;
+    bool narrow;
+    if (table) {
+        narrow = (meta & 0x7FFFFFu) <= kQuadTableMaxLen;
     } else {
-        const Philox4 ra = philox4x32_10(seed_a >> 1, act, 0u, kTagPair, key0);
-        const Philox4 rb = philox4x32_10(seed_b >> 1, act, 0u, kTagPair, key0);
-        const bool odd_a = seed_a & 1u, odd_b = seed_b & 1u;
-        lo_a = odd_a ? ra.z : ra.x;
-        hi_a = odd_a ? ra.w : ra.y;
-        lo_b = odd_b ? rb.z : rb.x;
-        hi_b = odd_b ? rb.w : rb.y;
+        const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
+        narrow = d.flags() & 16;
     }
-    const double ua = uniform52(lo_a, hi_a), ub = uniform52(lo_b, hi_b);
+    uint32_t hi_a, hi_b;
+    double ua, ub;
+    if (narrow) {
+        draw32x2(seed_a, seed_b, 0u, 0u, act, kTagQuad, key0, hi_a, hi_b);
+        ua = uniform32(hi_a);
+        ub = uniform32(hi_b);
+    } else {
+        uint32_t lo_a, lo_b;
+        if (paired) {  // seeds {2k, 2k+1}: one block, words 0-1 / 2-3
+            const Philox4 r = philox4x32_10(seed_a >> 1, act, 0u, kTagPair, key0);
+            lo_a = r.x;
+            hi_a = r.y;
+            lo_b = r.z;
+            hi_b = r.w;
+        } else {
+            const Philox4 ra = philox4x32_10(seed_a >> 1, act, 0u, kTagPair, key0);
+            const Philox4 rb = philox4x32_10(seed_b >> 1, act, 0u, kTagPair, key0);
+            const bool odd_a = seed_a & 1u, odd_b = seed_b & 1u;
+            lo_a = odd_a ? ra.z : ra.x;
+            hi_a = odd_a ? ra.w : ra.y;
+            lo_b = odd_b ? rb.z : rb.x;
+            hi_b = odd_b ? rb.w : rb.y;
+        }
+        ua = uniform52(lo_a, hi_a);
+        ub = uniform52(lo_b, hi_b);
+    }
     if (kind == MCDP_DIST_EXPONENTIAL) {
         // inverse CDF of the exponential truncated to [0, max_scale]: the law of the
         // reference's rejection loop (_core.cpp:83-89), without the loop.

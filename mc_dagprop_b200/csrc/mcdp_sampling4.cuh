@@ -14,11 +14,27 @@
 namespace mcdp {
 
 // `quad`: the lane's seeds are s, s+1, s+2, s+3 with s even, i.e. two aligned PAIR blocks (s >> 1 and
-// (s + 2) >> 1) serve all four samples.
+// (s + 2) >> 1) serve all four samples; `quad4`: additionally s is a multiple of four, so ONE QUAD block
+// (s >> 2) serves all four.
 struct Seeds4 {
     uint32_t s[4];
-    bool quad;
+    bool quad, quad4;
 };
+
+// one 32-bit draw per sample from QUAD-style blocks with tag `tag`, draw index j[i]
+__device__ __forceinline__ void draw32x4(const Seeds4& sd, bool same_j, const uint32_t (&j)[4], uint32_t act, uint32_t tag,
+                                         const PhiloxKeys& key0, uint32_t (&w)[4]) {
+    if (sd.quad4 && same_j) {
+        const Philox4 r = philox4x32_10(sd.s[0] >> 2, act, j[0], tag, key0);
+        w[0] = r.x;
+        w[1] = r.y;
+        w[2] = r.z;
+        w[3] = r.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = philox_word(philox4x32_10(sd.s[i] >> 2, act, j[i], tag, key0), sd.s[i] & 3u);
+    }
+}
 
 // one 64-bit draw per sample from PAIR-style blocks with tag `tag`, draw index j[i]
 __device__ __forceinline__ void draw64x4(const Seeds4& sd, bool same_j, const uint32_t (&j)[4], uint32_t act, uint32_t tag,
@@ -130,7 +146,11 @@ __device__ __forceinline__ void erlang_draw4(const DistView<SMEM>& d, int varian
                                              const uint32_t (&j)[4], uint32_t act, const PhiloxKeys& key0, uint32_t log_tab,
                                              double (&y)[4]) {
     uint32_t w0[4], w1[4], w2[4] = {0u, 0u, 0u, 0u}, w3[4] = {0u, 0u, 0u, 0u};
-    if (variant <= 2 || variant == 4) {  // <= 64 bits per sample: PAIR-style blocks
+    if (variant == 2) {  // one 32-bit uniform per sample: a QUAD-style block
+        draw32x4(sd, same_j, j, act, kTagErlang, key0, w0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w1[i] = 0u;
+    } else if (variant == 1 || variant == 4) {  // 64 bits per sample: PAIR-style blocks
         draw64x4(sd, same_j, j, act, kTagErlang, key0, w0, w1);
     } else {
 #pragma unroll
@@ -161,7 +181,7 @@ __device__ __forceinline__ void erlang_variate4(const DistView<SMEM>& d, const S
 #pragma unroll
             for (int i = 0; i < 4; ++i) j[i] += need[i] ? 1u : 0u;
             double y[4];
-            erlang_draw4<SMEM>(d, variant, sd, j[0] == j[1] && j[2] == j[3], j, act, key0, log_tab, y);
+            erlang_draw4<SMEM>(d, variant, sd, j[0] == j[1] && j[1] == j[2] && j[2] == j[3], j, act, key0, log_tab, y);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (need[i]) {
@@ -175,22 +195,35 @@ __device__ __forceinline__ void erlang_variate4(const DistView<SMEM>& d, const S
     }
 }
 
-// Marsaglia-Tsang for four samples: first attempts straight-line, then ONE warp-wide retry loop in which
-// every lane retries its first pending sample (gamma_variate2 widened; same SOLO blocks per attempt).
+// Marsaglia-Tsang for four samples: the first attempts come out of the two GAM0 blocks of the lane's seed pairs (one
+// Box-Muller pair each: cos branch even seed, sin branch odd seed) and run in lockstep; then ONE warp-wide retry loop
+// in which every lane retries its first pending sample from that sample's SOLO blocks (gamma_variate2 widened).
 template <bool SMEM>
 __device__ __forceinline__ void gamma_variate4(const DistView<SMEM>& d, const Seeds4& sd, uint32_t act,
                                                const PhiloxKeys& key0, double (&x)[4]) {
+    float nf[4];
+    uint32_t wacc[4], wboost[4] = {0u, 0u, 0u, 0u};
+    if (sd.quad) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const Philox4 blk = philox4x32_10(sd.s[2 * h] >> 1, act, 0u, kTagGam0, key0);
+            float r, ang;
+            box_muller_polar(blk.x, blk.y, r, ang);
+            nf[2 * h] = r * cos_approx(ang);
+            nf[2 * h + 1] = r * sin_approx(ang);
+            wacc[2 * h] = blk.z;
+            wacc[2 * h + 1] = blk.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gam0_take(philox4x32_10(sd.s[i] >> 1, act, 0u, kTagGam0, key0), sd.s[i], nf[i], wacc[i]);
+    }
+    if (d.flags() & 1) {
+        const uint32_t j0[4] = {0u, 0u, 0u, 0u};
+        draw32x4(sd, true, j0, act, kTagGbst, key0, wboost);
+    }
     bool need[4];
-    {
-        const Philox4 wa = philox4x32_10(sd.s[0], act, 0u, kTagSolo, key0);
-        const Philox4 wb = philox4x32_10(sd.s[1], act, 0u, kTagSolo, key0);
-        gamma_eval2<SMEM>(d, wa, wb, x[0], x[1], need[0], need[1]);
-    }
-    {
-        const Philox4 wc = philox4x32_10(sd.s[2], act, 0u, kTagSolo, key0);
-        const Philox4 wd = philox4x32_10(sd.s[3], act, 0u, kTagSolo, key0);
-        gamma_eval2<SMEM>(d, wc, wd, x[2], x[3], need[2], need[3]);
-    }
+    gamma_first_attempts<SMEM, 4>(d, nf, wacc, wboost, x, need);
 #pragma unroll
     for (int i = 0; i < 4; ++i) need[i] = !need[i];
     uint32_t t[4] = {1u, 1u, 1u, 1u};
@@ -239,19 +272,28 @@ __device__ __forceinline__ void sample_extra4(uint32_t meta, uint32_t tab_off, t
         for (int i = 0; i < 4; ++i) e[i] = __dmul_rn(x[i], base);
         return;
     }
-    // one 64-bit draw per sample
-    uint32_t lo[4], hi[4];
-    const uint32_t j0[4] = {0u, 0u, 0u, 0u};
-    draw64x4(sd, true, j0, act, kTagPair, key0, lo, hi);
+    // One uniform per sample: 32 bits from ONE QUAD block for the whole lane-quad when the contract's width rule
+    // allows (tables of <= 4096 entries, exponentials with flags bit4), else 64 bits from two PAIR blocks.
+    uint32_t hi[4];
     double u[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) u[i] = uniform52(lo[i], hi[i]);
+    const uint32_t j0[4] = {0u, 0u, 0u, 0u};
     if (kind == MCDP_DIST_EXPONENTIAL) {
         // inverse CDF of the exponential truncated to [0, max_scale] (see sample_extra2; _core.cpp:83-89)
         const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
+        const int flags = d.flags();
+        if (flags & 16) {
+            draw32x4(sd, true, j0, act, kTagQuad, key0, hi);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) u[i] = uniform32(hi[i]);
+        } else {
+            uint32_t lo[4];
+            draw64x4(sd, true, j0, act, kTagPair, key0, lo, hi);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) u[i] = uniform52(lo[i], hi[i]);
+        }
         const double lam = d.p(0), mx = d.p(1), F = d.p(2);
         double x[4];
-        if (d.flags() & 2) {
+        if (flags & 2) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) x[i] = lam * neg_log1m(u[i] * F, true, log_tab);
         } else {
@@ -264,6 +306,16 @@ __device__ __forceinline__ void sample_extra4(uint32_t meta, uint32_t tab_off, t
             e[i] = __dmul_rn(x[i], base);
         }
         return;
+    }
+    if ((meta & 0x7FFFFFu) <= kQuadTableMaxLen) {
+        draw32x4(sd, true, j0, act, kTagQuad, key0, hi);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = uniform32(hi[i]);
+    } else {
+        uint32_t lo[4];
+        draw64x4(sd, true, j0, act, kTagPair, key0, lo, hi);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = uniform52(lo[i], hi[i]);
     }
     // empirical tables (pool block layout: see sample_extra2)
     const uint32_t g = (meta >> 24) & 31u, len8 = (meta & 0x7FFFFFu) * 8u;

@@ -191,7 +191,7 @@ class OracleSim(_SimBase):
         return r, c
 
     def run_many_spec(self, seeds, stream_key=0, realized=True, durations=True, cause=True):
-        """Device generator contract mcdp-philox-v1 (not reference behaviour) + reference propagation."""
+        """Device generator contract mcdp-philox-v2 (not reference behaviour) + reference propagation."""
         seeds = _a(seeds, np.int32)
         r, d, c = self._alloc(seeds.size, realized, durations, cause)
         self._lib.mcdp_or_sim_run_many_spec(self._h, _pad(seeds), seeds.size, stream_key, self._p(r, C.c_double),

@@ -463,7 +463,7 @@ int32_t mcdp_or_sim_run_injected(mcdp_or_sim* s, const double* durations, int64_
 }
 
 /* ======================================================================== */
-/* Part 2: device generator contract "mcdp-philox-v1"   */
+/* Part 2: device generator contract "mcdp-philox-v2"   */
 /* NOT reference behaviour: the reference stream is Xoshiro256++ (Part 1).   */
 /* ======================================================================== */
 
@@ -489,7 +489,14 @@ void mcdp_or_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_
 #define SPEC_TAG_SOLO 0x534F4C4Fu /* 'SOLO' */
 #define SPEC_KEY1 0x4D434450u     /* 'MCDP' */
 #define SPEC_TAG_ERLANG 0x45524C47u /* 'ERLG' */
+#define SPEC_TAG_QUAD 0x51554144u /* 'QUAD' */
+#define SPEC_TAG_GAM0 0x47414D30u /* 'GAM0' */
+#define SPEC_TAG_GBST 0x47425354u /* 'GBST' */
 #define SPEC_GAMMA_MAX_ATTEMPTS 65536u
+/* width rule of v2: a 32-bit uniform from a QUAD block for tables of at most 4096 entries and exponentials with
+ * max_scale <= 16 lambda; 64 bits from a PAIR block otherwise */
+#define SPEC_QUAD_TABLE_MAX_LEN 4096
+#define SPEC_QUAD_EXP_MAX_RATIO 16.0
 
 static double spec_u52(uint64_t x) { return ((double)(x >> 12) + 0.5) * 0x1p-52; }
 static double spec_u32(uint32_t w) { return ((double)w + 0.5) * 0x1p-32; }
@@ -504,13 +511,24 @@ static uint64_t spec_pair_bits(uint32_t act, uint32_t seed, uint32_t j, uint32_t
     return (seed & 1u) ? (((uint64_t)r[3] << 32) | r[2]) : (((uint64_t)r[1] << 32) | r[0]);
 }
 
+/* 32 random bits of (activity, seed, draw j): word (seed & 3) of the block of the seed quad {4k .. 4k+3} */
+static uint32_t spec_quad_word(uint32_t act, uint32_t seed, uint32_t j, uint32_t tag, uint32_t stream_key) {
+    const uint32_t ctr[4] = {seed >> 2, act, j, tag};
+    const uint32_t key[2] = {stream_key, SPEC_KEY1};
+    uint32_t r[4];
+    mcdp_or_philox4x32_10(ctr, key, r);
+    return r[seed & 3u];
+}
+
 static double spec_sample_extra(const or_dist* d, double base, uint32_t act, uint32_t seed, uint32_t stream_key) {
     switch (d->kind) {
         case MCDP_OR_CONSTANT:
             return base * d->p0;
         case MCDP_OR_EXPONENTIAL: {
             /* inverse CDF of the law truncated to [0, max_scale] == law of the reference's rejection loop */
-            const double u = spec_u52(spec_pair_bits(act, seed, 0u, stream_key));
+            const double u = d->p1 <= SPEC_QUAD_EXP_MAX_RATIO * d->p0
+                                 ? spec_u32(spec_quad_word(act, seed, 0u, SPEC_TAG_QUAD, stream_key))
+                                 : spec_u52(spec_pair_bits(act, seed, 0u, stream_key));
             double x = -d->p0 * log1p(-u * d->exp_F);
             if (x > d->p1) x = d->p1;
             return x * base;
@@ -518,7 +536,12 @@ static double spec_sample_extra(const or_dist* d, double base, uint32_t act, uin
         case MCDP_OR_EMP_ABS:
         case MCDP_OR_EMP_REL: {
             int64_t idx = 0;
-            if (d->cp_n) idx = or_lower_bound(d->cp, d->cp_n, spec_u52(spec_pair_bits(act, seed, 0u, stream_key)));
+            if (d->cp_n) {
+                const double u = d->cp_n <= SPEC_QUAD_TABLE_MAX_LEN
+                                     ? spec_u32(spec_quad_word(act, seed, 0u, SPEC_TAG_QUAD, stream_key))
+                                     : spec_u52(spec_pair_bits(act, seed, 0u, stream_key));
+                idx = or_lower_bound(d->cp, d->cp_n, u);
+            }
             return d->kind == MCDP_OR_EMP_ABS ? d->vals[idx] : d->vals[idx] * base;
         }
         case MCDP_OR_GAMMA: {
@@ -528,12 +551,16 @@ static double spec_sample_extra(const or_dist* d, double base, uint32_t act, uin
             const double twice = 2.0 * d->p0;
             if (twice == floor(twice) && twice >= 1.0 && twice <= 8.0 && twice != 7.0) {
                 /* exact transformation for 2*shape in {1..6, 8}: k = floor(shape) unit exponentials (+ half a squared
-                 * Box-Muller normal); <= 2 uniforms: the seed's half of block (seed>>1, act, j, 'ERLG'), else the
-                 * four words of block (seed, act, j, 'ERLG'); draw j+1 when x > max_scale */
+                 * Box-Muller normal); one uniform (shape 1): the seed's word of block (seed>>2, act, j, 'ERLG'); two:
+                 * the seed's half of block (seed>>1, act, j, 'ERLG'); else the four words of block (seed, act, j,
+                 * 'ERLG'); draw j+1 when x > max_scale */
                 const int k = (int)floor(d->p0), half = ((int)twice) & 1;
                 for (uint32_t j = 0; j < SPEC_GAMMA_MAX_ATTEMPTS; ++j) {
                     uint32_t w[4], r[4];
-                    if (k + 2 * half <= 2) {
+                    if (k + 2 * half == 1) {
+                        w[0] = spec_quad_word(act, seed, j, SPEC_TAG_ERLANG, stream_key);
+                        w[1] = w[2] = w[3] = 0u;
+                    } else if (k + 2 * half <= 2) {
                         const uint32_t ctr[4] = {seed >> 1, act, j, SPEC_TAG_ERLANG};
                         mcdp_or_philox4x32_10(ctr, key, r);
                         w[0] = (seed & 1u) ? r[2] : r[0];
@@ -560,22 +587,37 @@ static double spec_sample_extra(const or_dist* d, double base, uint32_t act, uin
                 return x * base;
             }
             for (uint32_t t = 0; t < SPEC_GAMMA_MAX_ATTEMPTS; ++t) {
-                const uint32_t ctr[4] = {seed, act, t, SPEC_TAG_SOLO};
-                uint32_t w[4];
-                mcdp_or_philox4x32_10(ctr, key, w);
-                /* Box-Muller normal: radius from a 23-bit uniform, angle 2 pi * int32(w1) / 2^32.  The device
+                /* Box-Muller normal: radius from a 23-bit uniform, angle 2 pi * int32(w) / 2^32.  The device
                  * evaluates this deviate and the two acceptance comparisons with fp32 hardware
-                 * approximations; this restatement is the exact-arithmetic definition. */
-                const double n = sqrt(-2.0 * log(spec_u23(w[0]))) *
-                                 cos(6.283185307179586476925286766559 * (double)(int32_t)w[1] * 0x1p-32);
+                 * approximations; this restatement is the exact-arithmetic definition.
+                 * Attempt 0: block (seed>>1, act, 0, 'GAM0') holds ONE Box-Muller pair for the seed pair -- radius
+                 * word 0, angle word 1; the even seed takes the cos branch and accept word 2, the odd seed the sin
+                 * branch and accept word 3 -- and the shape < 1 boost uniform is the seed's word of block
+                 * (seed>>2, act, 0, 'GBST').  Attempt t >= 1: block (seed, act, t, 'SOLO'): radius, angle (cos
+                 * branch), accept, boost. */
+                uint32_t w[4];
+                double n, u, boost_u;
+                if (t == 0u) {
+                    const uint32_t ctr[4] = {seed >> 1, act, 0u, SPEC_TAG_GAM0};
+                    mcdp_or_philox4x32_10(ctr, key, w);
+                    const double ang = 6.283185307179586476925286766559 * (double)(int32_t)w[1] * 0x1p-32;
+                    n = sqrt(-2.0 * log(spec_u23(w[0]))) * ((seed & 1u) ? sin(ang) : cos(ang));
+                    u = spec_u23((seed & 1u) ? w[3] : w[2]);
+                    boost_u = d->p0 != d->malpha ? spec_u23(spec_quad_word(act, seed, 0u, SPEC_TAG_GBST, stream_key)) : 1.0;
+                } else {
+                    const uint32_t ctr[4] = {seed, act, t, SPEC_TAG_SOLO};
+                    mcdp_or_philox4x32_10(ctr, key, w);
+                    n = sqrt(-2.0 * log(spec_u23(w[0]))) * cos(6.283185307179586476925286766559 * (double)(int32_t)w[1] * 0x1p-32);
+                    u = spec_u23(w[2]);
+                    boost_u = spec_u23(w[3]);
+                }
                 double v = 1.0 + d->a2 * n;
                 if (v <= 0.0) continue;
                 v = v * v * v;
-                const double u = spec_u23(w[2]);
                 const double n2 = n * n;
                 if (u > 1.0 - 0.0331 * n2 * n2 && log(u) > 0.5 * n2 + a1 * (1.0 - v + log(v))) continue;
                 x = a1 * v * d->p1;
-                if (d->p0 != d->malpha) x *= pow(spec_u23(w[3]), 1.0 / d->p0);
+                if (d->p0 != d->malpha) x *= pow(boost_u, 1.0 / d->p0);
                 if (x > d->p2) continue;
                 return x * base;
             }

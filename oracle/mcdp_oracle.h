@@ -12,7 +12,7 @@
  * load this library.  The product (mc_dagprop_b200) never does.
  *
  * The second half ("spec" functions) restates the *device* generator contract
- * mcdp-philox-v1 so that the CUDA kernels can be checked
+ * mcdp-philox-v2 so that the CUDA kernels can be checked
  * draw-for-draw; it is not reference behaviour and is labelled as such.
  */
 #ifndef MCDP_ORACLE_H
@@ -73,7 +73,7 @@ int32_t mcdp_or_sim_run_many(mcdp_or_sim* sim, const int32_t* seeds, int64_t n, 
 int32_t mcdp_or_sim_run_injected(mcdp_or_sim* sim, const double* durations, int64_t n, double* realized,
                                  int32_t* cause);
 
-/* ---- device generator contract mcdp-philox-v1 (NOT reference behaviour) - */
+/* ---- device generator contract mcdp-philox-v2 (NOT reference behaviour) - */
 void mcdp_or_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* durations per the device contract, then the reference propagation. */
 int32_t mcdp_or_sim_run_many_spec(mcdp_or_sim* sim, const int32_t* seeds, int64_t n, uint32_t stream_key,

@@ -7,7 +7,7 @@ line table nvdisasm prints for the SAME build of libmcdp_b200.so.
 """
 import collections, csv, io, os, re, subprocess, sys, tempfile
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.environ.get("MCDP_ROOT") or os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # MCDP_ROOT: a checkout of the captured build
 
 def sass_lines(so, kernel_sub):
     tmp = tempfile.mkdtemp()

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = capi.lib()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.mcdp_abi_version() == 3
+    assert lib.mcdp_abi_version() == 4
 
 
 def test_no_cpu_execution_path():
@@ -160,13 +160,15 @@ def test_launch_shape_of_both_kernels():
     assert plan.launch_shape(129)["grid"] == 2 and plan.launch_shape(128)["grid"] == 1 and plan.launch_shape(1)["grid"] == 1
     plan.set_option(capi.OPT_SAMPLES_PER_LANE, 2)
     assert plan.launch_shape(129)["grid"] == 3
-    # multi-batch reduced launches (more 64-sample batches than warp slots) stay on the pair path
-    plan.set_option(capi.OPT_SAMPLES_PER_LANE, 4)
+    # reduced launches of any size are single-batch launches of the quad kernel (it stages its statistics per warp)
+    plan.set_option(capi.OPT_SAMPLES_PER_LANE, 0)
     plan.set_option(capi.OPT_WARPS_PER_GROUP, 0)
     plan.set_option(capi.OPT_GROUPS_PER_CTA, 0)
     big = plan.launch_shape(1 << 20, reduced=True, n_bins=64)
-    assert big["batches"] > 1 and big["samples_per_lane"] == 2
+    assert big["samples_per_lane"] == 4 and big["grid"] * big["groups_per_cta"] * 128 >= 1 << 20
     assert plan.launch_shape(1 << 15, reduced=True, n_bins=64)["samples_per_lane"] == 4
+    full = plan.launch_shape(1 << 15, reduced=False)
+    assert plan.launch_shape(1 << 15, reduced=True, n_bins=64)["smem_bytes"] > full["smem_bytes"]  # + the staging areas
     with pytest.raises(RuntimeError, match="samples per lane"):
         plan.set_option(capi.OPT_SAMPLES_PER_LANE, 3)
 
@@ -207,11 +209,14 @@ def test_launch_shape_invariants(gen):
                 for reduced in (False, True):
                     s = plan.launch_shape(n, reduced, 64 if reduced else 0)
                     k = s["samples_per_lane"]
-                    assert k in (2, 4) and (spl == 0 or k == spl or s["batches"] > 1)
+                    assert k in (2, 4) and (spl == 0 or k == spl)
                     assert s["threads"] == 32 * s["warps_per_group"] * s["groups_per_cta"]
                     assert s["threads"] <= (640 if k == 4 else 512) and 1 <= s["groups_per_cta"] <= 15
-                    assert s["grid"] * s["groups_per_cta"] * 32 * k * s["batches"] >= n
-                    assert (s["grid"] - 1) * s["groups_per_cta"] * 32 * k * s["batches"] < n  # no empty CTA
+                    c = s["cluster"]
+                    assert c in (1, 2, 4, 8) and s["grid"] % c == 0
+                    groups = s["grid"] // c * s["groups_per_cta"]
+                    assert groups * 32 * k >= n
+                    assert (s["grid"] // c - 1) * s["groups_per_cta"] * 32 * k < n  # no empty CTA
                     assert s["smem_bytes"] <= 227 * 1024
-                    if s["batches"] > 1:
-                        assert reduced and k == 2
+                    if c > 1:  # a cluster shares ONE group: quad kernel, one group per CTA, several warps, few groups
+                        assert k == 4 and s["groups_per_cta"] == 1 and s["warps_per_group"] > 1 and s["grid"] <= 148

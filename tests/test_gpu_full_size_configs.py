@@ -60,8 +60,9 @@ def test_full_size_config_parity_and_properties(name):
     assert np.array_equal(st.hist.astype(np.int64), cnt)
 
 
-def test_reduced_mode_multi_batch_folding_matches_single_batch():
-    """Enough samples that groups fold several 64-sample batches per event (MULTI kernel variant)."""
+def test_reduced_mode_many_waves_matches_full_outputs():
+    """Several waves of sample groups per launch: every warp stages and folds its own statistics, the global
+    accumulators add up to the statistics of the full outputs."""
     dag, dists = synth.random_dag(80, 3, max_delay=60.0), synth.mixed_small_dists()
     plan = capi.Plan(dag, dists, device=0)
     n = 148 * 32 * 64 * 3 + 100  # > 3 batches per warp slot

@@ -220,3 +220,79 @@ def test_quad_machine_filling_launch_matches_oracle_and_pair(name, n):
     assert np.array_equal(_bits(r_o), _bits(r_s)) and np.array_equal(c_o, c_s)
     r_p, d_p, c_p = _plan(dag, dists, 2).run_many_host((seed0 + cols).astype(np.int32))
     assert np.array_equal(_bits(d_p), _bits(d_s)) and np.array_equal(_bits(r_p), _bits(r_s)) and np.array_equal(c_p, c_s)
+
+
+# ---- thread-block clusters: the CTAs of a cluster share one sample group and split its levels ------------------------
+
+@pytest.mark.parametrize("cluster", [2, 4, 8])
+@pytest.mark.parametrize("wpg", [2, 5, 20])
+def test_cluster_launch_is_bit_identical(cluster, wpg):
+    """Same bits with and without the cluster split, for injection, fused sampling (wide levels, long events that
+    run through continuation chunks, orphan activities) and ragged sample counts."""
+    dag = synth.random_dag(1200, 5, max_fan_in=40)
+    dists = _all_kinds_dists()
+    osim = oracle.OracleSim(dag, dists)
+    seeds = np.arange(-5, 300, dtype=np.int32)  # 305 samples: three groups, the last one ragged
+    _, dur, _ = osim.run_many(seeds)
+    r_o, c_o = osim.run_injected(dur)
+    ref = _plan(dag, dists, 4, wpg=wpg, gpc=1)
+    ref.set_option(capi.OPT_CLUSTER_SIZE, 1)
+    plan = _plan(dag, dists, 4, wpg=wpg, gpc=1)
+    plan.set_option(capi.OPT_CLUSTER_SIZE, cluster)
+    sh = plan.launch_shape(seeds.size)
+    assert sh["cluster"] == cluster and sh["grid"] == 3 * cluster
+    r_d, c_d = plan.run_injected_host(dur)
+    assert np.array_equal(_bits(r_o), _bits(r_d)) and np.array_equal(c_o, c_d)
+    a, b = ref.run_many_host(seeds), plan.run_many_host(seeds)
+    for x, y in zip(a, b):
+        assert np.array_equal(np.ascontiguousarray(x).view(np.uint8), np.ascontiguousarray(y).view(np.uint8))
+
+
+@pytest.mark.parametrize("cluster", [2, 8])
+def test_cluster_launch_reduced_statistics(cluster):
+    dag = synth.random_dag(900, 6, max_delay=60.0, max_fan_in=12)
+    dists = synth.mixed_small_dists()
+    seeds = np.arange(3, 3 + 700, dtype=np.int32)
+    th = (1.0, 10.0)
+    ref = _plan(dag, dists, 4, wpg=4, gpc=1)
+    ref.set_option(capi.OPT_CLUSTER_SIZE, 1)
+    plan = _plan(dag, dists, 4, wpg=4, gpc=1)
+    plan.set_option(capi.OPT_CLUSTER_SIZE, cluster)
+    a = ref.run_reduced_host(seeds, thresholds=th, n_bins=20, hist_range=(0.0, 60.0))
+    b, act, none = plan.run_attribution_host(seeds, thresholds=th, n_bins=20, hist_range=(0.0, 60.0))
+    np.testing.assert_allclose(b.sum, a.sum, rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(b.sumsq, a.sumsq, rtol=1e-12, atol=1e-9)
+    assert np.array_equal(a.late, b.late) and np.array_equal(a.hist, b.hist)
+    _, act1, none1 = ref.run_attribution_host(seeds, thresholds=th, n_bins=20, hist_range=(0.0, 60.0))
+    assert np.array_equal(act, act1) and np.array_equal(none, none1)
+
+
+def test_auto_rule_clusters_small_launches_only():
+    dag, dists = synth.c3_network()
+    plan = capi.Plan(dag, dists, device=0)
+    small, full = plan.launch_shape(2048), plan.launch_shape(18944)
+    assert small["samples_per_lane"] == 4 and small["cluster"] == 8 and small["grid"] == 16 * 8
+    assert full["cluster"] == 1 and full["grid"] == 148
+    one = plan.launch_shape(1)
+    assert one["cluster"] == 8 and one["grid"] == 8
+
+
+@pytest.mark.parametrize("n_bins", [1, 7, 64, 65, 100])
+def test_quad_histogram_staged_and_direct_paths(n_bins):
+    """Up to 64 bins the warp stages 16-bit pair counts in shared memory, beyond that it aggregates with match.any:
+    both equal the histogram of the full outputs (ragged sample count, event count not a multiple of the staging
+    depth)."""
+    dag = synth.random_dag(203, 9, max_delay=60.0)
+    dists = synth.mixed_small_dists()
+    seeds = np.arange(50, 50 + 333, dtype=np.int32)
+    plan = _plan(dag, dists, 4)
+    st = plan.run_reduced_host(seeds, thresholds=(0.0, 2.5, 59.0, 1e9), n_bins=n_bins, hist_range=(0.0, 60.0))
+    r, _, _ = plan.run_many_host(seeds)
+    delay = r - np.asarray(dag.earliest)[None, :]
+    bins = np.clip(np.floor((delay - 0.0) * (n_bins / 60.0)).astype(np.int64), 0, n_bins - 1)
+    ref = np.stack([np.bincount(bins[:, e], minlength=n_bins) for e in range(plan.E)])
+    assert np.array_equal(st.hist.astype(np.int64), ref)
+    for i, t in enumerate((0.0, 2.5, 59.0, 1e9)):
+        assert np.array_equal(st.late[i], (delay > t).sum(0).astype(np.uint64))
+    np.testing.assert_allclose(st.sum, delay.sum(0), rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(st.sumsq, (delay * delay).sum(0), rtol=1e-12, atol=1e-9)
