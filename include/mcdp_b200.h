@@ -204,6 +204,31 @@ int32_t mcdp_run_attribution_host(mcdp_plan* plan, const int32_t* seeds, int64_t
                                   double* sum, double* sumsq, unsigned long long* late, uint32_t* hist,
                                   unsigned long long* cause_act, unsigned long long* cause_none);
 
+/* ---- several devices behind one call (additive) ----
+ * The reference's only scale-out hook is run_many (_core.cpp:355-361: a loop over independent seeds) plus one
+ * Simulator per thread (test/test_simulator.py:201-215).  A plan set compiles the DagContext once and holds one
+ * device-resident copy per listed device (a device may be listed more than once); every *_multi call shards its
+ * seeds into contiguous blocks (whole 128-sample groups), one per device, and returns exactly what the single-device
+ * call returns: identical bits for full outputs and integer statistics, f64 sums to summation order.  Full outputs
+ * need no exchange (each device copies its rows into the caller's arrays); the reduced statistics are folded by a
+ * reduce-scatter over peer memory (device d sums slice d of every accumulator over all devices through NVLink peer
+ * mappings, fixed order) whose slices go straight to the caller -- it needs peer access between the devices. */
+typedef struct mcdp_planset mcdp_planset;
+int32_t mcdp_planset_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* dists, const int32_t* devices,
+                            int32_t n_devices, mcdp_planset** out); /* 1..16 devices */
+void mcdp_planset_destroy(mcdp_planset* set);
+int32_t mcdp_planset_size(const mcdp_planset* set);
+mcdp_plan* mcdp_planset_plan(mcdp_planset* set, int32_t i); /* borrowed: plan of the i-th listed device */
+int32_t mcdp_planset_set_option(mcdp_planset* set, int32_t option, int64_t value); /* on every plan of the set */
+int32_t mcdp_run_many_host_multi(mcdp_planset* set, const int32_t* seeds, int64_t n, double* realized, double* durations,
+                                 int32_t* cause);
+int32_t mcdp_run_injected_host_multi(mcdp_planset* set, const double* durations, int64_t n, double* realized, int32_t* cause);
+int32_t mcdp_run_reduced_host_multi(mcdp_planset* set, const int32_t* seeds, int64_t n, const mcdp_stats_desc* desc,
+                                    double* sum, double* sumsq, unsigned long long* late, uint32_t* hist);
+int32_t mcdp_run_attribution_host_multi(mcdp_planset* set, const int32_t* seeds, int64_t n, const mcdp_stats_desc* desc,
+                                        double* sum, double* sumsq, unsigned long long* late, uint32_t* hist,
+                                        unsigned long long* cause_act, unsigned long long* cause_none);
+
 void* mcdp_host_alloc(size_t bytes); /* pinned host memory, NULL on failure */
 void mcdp_host_free(void* p);
 

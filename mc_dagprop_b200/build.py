@@ -38,7 +38,7 @@ def _sources(*exts: str) -> list[str]:
 
 
 def build_lib(force: bool = False, verbose: bool = False) -> str:
-    deps = _sources(".cu", ".cuh", ".cpp", ".hpp", ".h")
+    deps = _sources(".cu", ".cuh", ".cpp", ".hpp", ".h", ".inl")
     deps = [d for d in deps if not d.endswith("pybind_core.cpp")]
     if force or _newer(LIB, deps):
         cmd = [NVCC, "-O3", "-std=c++17", *ARCH_FLAGS, "-lineinfo", "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-O3,-Wall",

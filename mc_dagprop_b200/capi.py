@@ -35,6 +35,8 @@ EXPORTED_SYMBOLS = (
     "mcdp_run_full_device", "mcdp_run_injected_device", "mcdp_run_reduced_device", "mcdp_transpose_f64_device",
     "mcdp_transpose_i32_device", "mcdp_run_many_host", "mcdp_run_injected_host", "mcdp_run_reduced_host",
     "mcdp_plan_get_chunks", "mcdp_plan_launch_shape", "mcdp_run_attribution_device", "mcdp_run_attribution_host", "mcdp_host_alloc", "mcdp_host_free",
+    "mcdp_planset_create", "mcdp_planset_destroy", "mcdp_planset_size", "mcdp_planset_plan", "mcdp_planset_set_option",
+    "mcdp_run_many_host_multi", "mcdp_run_injected_host_multi", "mcdp_run_reduced_host_multi", "mcdp_run_attribution_host_multi",
 )
 
 
@@ -100,6 +102,17 @@ def lib() -> C.CDLL:
         L.mcdp_run_reduced_host.argtypes = [vp, vp, i64, C.POINTER(StatsDesc), vp, vp, vp, vp]
         L.mcdp_run_attribution_device.argtypes = [vp, vp, i32, i64, C.POINTER(StatsDesc), vp, vp, vp, vp, vp, vp, vp]
         L.mcdp_run_attribution_host.argtypes = [vp, vp, i64, C.POINTER(StatsDesc), vp, vp, vp, vp, vp, vp]
+        L.mcdp_planset_create.argtypes = [C.POINTER(GraphDesc), C.POINTER(DistsDesc), vp, i32, C.POINTER(vp)]
+        L.mcdp_planset_destroy.argtypes = [vp]
+        L.mcdp_planset_destroy.restype = None
+        L.mcdp_planset_size.argtypes = [vp]
+        L.mcdp_planset_plan.argtypes = [vp, i32]
+        L.mcdp_planset_plan.restype = vp
+        L.mcdp_planset_set_option.argtypes = [vp, i32, i64]
+        L.mcdp_run_many_host_multi.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.mcdp_run_injected_host_multi.argtypes = [vp, vp, i64, vp, vp]
+        L.mcdp_run_reduced_host_multi.argtypes = [vp, vp, i64, C.POINTER(StatsDesc), vp, vp, vp, vp]
+        L.mcdp_run_attribution_host_multi.argtypes = [vp, vp, i64, C.POINTER(StatsDesc), vp, vp, vp, vp, vp, vp]
         L.mcdp_host_alloc.argtypes = [C.c_size_t]
         L.mcdp_host_alloc.restype = vp
         L.mcdp_host_free.argtypes = [vp]
@@ -177,30 +190,36 @@ def make_stats_desc(thresholds=(), n_bins=0, hist_range=(0.0, 1.0)) -> StatsDesc
     return d
 
 
+def _descs(dag, dists):
+    """Flat descriptions -> (GraphDesc, DistsDesc, arrays that must stay alive during the call)."""
+    keep = [
+        _np(dag.earliest, np.float64), _np(dag.act_idx, np.int32), _np(dag.act_base, np.float64),
+        _np(dag.act_type, np.int32), _np(dag.prec_target, np.int32), _np(dag.prec_off, np.int64),
+        _np(dag.pred_src, np.int32), _np(dag.pred_act, np.int32),
+        _np(dists.dist_type, np.int32), _np(dists.kind, np.int32), _np(dists.p0, np.float64),
+        _np(dists.p1, np.float64), _np(dists.p2, np.float64), _np(dists.tab_off, np.int64),
+        _np(dists.tab_values, np.float64), _np(dists.tab_weights, np.float64),
+    ]
+    if keep[5].size == 0:
+        keep[5] = np.zeros(1, np.int64)
+    if keep[13].size == 0:
+        keep[13] = np.zeros(1, np.int64)
+    g = GraphDesc(keep[0].size, keep[0].ctypes.data, keep[1].size, keep[1].ctypes.data, keep[2].ctypes.data,
+                  keep[3].ctypes.data, keep[4].size, keep[4].ctypes.data, keep[5].ctypes.data,
+                  keep[6].ctypes.data, keep[7].ctypes.data, float(dag.max_delay))
+    d = DistsDesc(keep[8].size, keep[8].ctypes.data, keep[9].ctypes.data, keep[10].ctypes.data,
+                  keep[11].ctypes.data, keep[12].ctypes.data, keep[13].ctypes.data, keep[14].ctypes.data,
+                  keep[15].ctypes.data)
+    return g, d, keep
+
+
 class Plan:
     """A compiled, device-resident DAG + generator (``mcdp_plan``): the counterpart of a constructed
     reference ``Simulator`` (``_core.cpp:193-307``)."""
 
     def __init__(self, dag, dists, device: int = 0):
         L = lib()
-        keep = [
-            _np(dag.earliest, np.float64), _np(dag.act_idx, np.int32), _np(dag.act_base, np.float64),
-            _np(dag.act_type, np.int32), _np(dag.prec_target, np.int32), _np(dag.prec_off, np.int64),
-            _np(dag.pred_src, np.int32), _np(dag.pred_act, np.int32),
-            _np(dists.dist_type, np.int32), _np(dists.kind, np.int32), _np(dists.p0, np.float64),
-            _np(dists.p1, np.float64), _np(dists.p2, np.float64), _np(dists.tab_off, np.int64),
-            _np(dists.tab_values, np.float64), _np(dists.tab_weights, np.float64),
-        ]
-        if keep[5].size == 0:
-            keep[5] = np.zeros(1, np.int64)
-        if keep[13].size == 0:
-            keep[13] = np.zeros(1, np.int64)
-        g = GraphDesc(keep[0].size, keep[0].ctypes.data, keep[1].size, keep[1].ctypes.data, keep[2].ctypes.data,
-                      keep[3].ctypes.data, keep[4].size, keep[4].ctypes.data, keep[5].ctypes.data,
-                      keep[6].ctypes.data, keep[7].ctypes.data, float(dag.max_delay))
-        d = DistsDesc(keep[8].size, keep[8].ctypes.data, keep[9].ctypes.data, keep[10].ctypes.data,
-                      keep[11].ctypes.data, keep[12].ctypes.data, keep[13].ctypes.data, keep[14].ctypes.data,
-                      keep[15].ctypes.data)
+        g, d, _keep = _descs(dag, dists)
         h = C.c_void_p()
         self._h = None
         _check(L.mcdp_plan_create(C.byref(g), C.byref(d), int(device), C.byref(h)))
@@ -310,3 +329,71 @@ class Plan:
                            stream=None):
         _check(lib().mcdp_run_reduced_device(self._h, _ptr(seeds), int(seed0), int(n), C.byref(desc), _ptr(sum),
                                              _ptr(sumsq), _ptr(late), _ptr(hist), _ptr(stream)))
+
+
+class PlanSet:
+    """One compiled plan per device (``mcdp_planset``): every call shards its seeds into contiguous blocks, one
+    per device, and returns what a single device returns.  ``devices`` may repeat an ordinal."""
+
+    def __init__(self, dag, dists, devices):
+        L = lib()
+        g, d, _keep = _descs(dag, dists)
+        self.devices = [int(x) for x in devices]
+        dev = np.asarray(self.devices, np.int32)
+        h = C.c_void_p()
+        self._h = None
+        _check(L.mcdp_planset_create(C.byref(g), C.byref(d), dev.ctypes.data, dev.size, C.byref(h)))
+        self._h = h
+        p0 = L.mcdp_planset_plan(h, 0)
+        self.E = int(L.mcdp_plan_node_count(p0))
+        self.A = int(L.mcdp_plan_activity_count(p0))
+
+    def close(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.mcdp_planset_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __len__(self):
+        return int(lib().mcdp_planset_size(self._h))
+
+    def set_option(self, option: int, value: int) -> None:
+        _check(lib().mcdp_planset_set_option(self._h, option, int(value)))
+
+    def run_many_host(self, seeds, realized=True, durations=True, cause=True, out=None):
+        seeds = _np(seeds, np.int32)
+        n = seeds.size
+        if out is None:
+            r = np.empty((n, self.E), np.float64) if realized else None
+            d = np.empty((n, self.A), np.float64) if durations else None
+            c = np.empty((n, self.E), np.int32) if cause else None
+        else:
+            r, d, c = out
+        _check(lib().mcdp_run_many_host_multi(self._h, seeds.ctypes.data, n, _ptr(r), _ptr(d), _ptr(c)))
+        return r, d, c
+
+    def run_injected_host(self, durations):
+        durations = np.ascontiguousarray(durations, np.float64)
+        n = durations.shape[0]
+        assert durations.size == n * self.A
+        r, c = np.empty((n, self.E), np.float64), np.empty((n, self.E), np.int32)
+        _check(lib().mcdp_run_injected_host_multi(self._h, durations.ctypes.data if durations.size else None, n,
+                                                  r.ctypes.data, c.ctypes.data))
+        return r, c
+
+    def run_attribution_host(self, seeds, thresholds=(), n_bins=0, hist_range=(0.0, 1.0), cause_counts=True):
+        seeds = _np(seeds, np.int32)
+        desc = make_stats_desc(thresholds, n_bins, hist_range)
+        s, q = np.zeros(self.E, np.float64), np.zeros(self.E, np.float64)
+        late = np.zeros((len(thresholds), self.E), np.uint64)
+        hist = np.zeros((self.E, n_bins), np.uint32)
+        cause_act = np.zeros(self.A, np.uint64) if cause_counts else None
+        cause_none = np.zeros(self.E, np.uint64) if cause_counts else None
+        _check(lib().mcdp_run_attribution_host_multi(self._h, seeds.ctypes.data, seeds.size, C.byref(desc), s.ctypes.data,
+                                                     q.ctypes.data, late.ctypes.data if late.size else None,
+                                                     hist.ctypes.data if hist.size else None, _ptr(cause_act), _ptr(cause_none)))
+        return Stats(seeds.size, s, q, late, hist, tuple(thresholds), tuple(hist_range)), cause_act, cause_none
+
+    def run_reduced_host(self, seeds, thresholds=(), n_bins=0, hist_range=(0.0, 1.0)) -> Stats:
+        return self.run_attribution_host(seeds, thresholds, n_bins, hist_range, cause_counts=False)[0]

@@ -7,9 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -116,7 +118,10 @@ struct HostSlot {
 }  // namespace
 
 struct mcdp_plan {
-    HostPlan host;
+    // the compiled plan on the host: shared by the plans of a plan set (one compile, one copy per device)
+    std::shared_ptr<HostPlan> host_sp;
+    HostPlan& host;
+    explicit mcdp_plan(std::shared_ptr<HostPlan> h) : host_sp(std::move(h)), host(*host_sp) {}
     int device = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
@@ -320,7 +325,9 @@ LaunchShape choose_shape_spl(const mcdp_plan* plan, int64_t n, bool reduced, int
             c = plan->cluster_size;
         } else {
             const int64_t chunks_per_level = h.n_levels > 0 ? int64_t(h.units.size() / size_t(kChunkUnits)) / h.n_levels : 0;
-            while (c < 8 && int64_t(2 * c) * n_groups <= plan->sm_count && int64_t(2 * c) * wpg <= chunks_per_level) c *= 2;
+            // (clusters of 8 CTAs of this size pack 16 to the machine, not 18: stay clear of a second wave)
+            while (c < 8 && int64_t(2 * c) * n_groups * 4 <= int64_t(plan->sm_count) * 3 && int64_t(2 * c) * wpg <= chunks_per_level)
+                c *= 2;
         }
         s.cluster = c;
         s.grid *= unsigned(c);
@@ -352,7 +359,7 @@ LaunchShape choose_shape(const mcdp_plan* plan, int64_t n, bool reduced = false,
     const LaunchShape s2 = choose_shape_spl(plan, n, reduced, n_bins, single_batch, 2, &e2);
     if (kAutoSamplesPerLane != 4) return s2;
     const LaunchShape s4 = choose_shape_spl(plan, n, reduced, n_bins, single_batch, 4, &e4);
-    return (s4.spl == 4 && (e4 >= kQuadMinFill || e4 > e2 + 0.1)) ? s4 : s2;
+    return (s4.spl == 4 && (e4 >= kQuadMinFill || e4 > e2 + 0.1 || (s4.cluster > 1 && e4 > e2))) ? s4 : s2;
 }
 
 template <typename K>
@@ -587,27 +594,18 @@ int32_t mcdp_device_count(void) {
     return n;
 }
 
-int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* dists, int32_t device, mcdp_plan** out) {
-    if (!graph || !dists || !out) return fail(MCDP_ERR_ARG, "null argument");
+}  // extern "C"
+
+namespace {
+// a plan on `device` (or host-only) around an already compiled host plan
+int32_t plan_from_host(std::shared_ptr<HostPlan> host, int32_t device, mcdp_plan** out) {
     *out = nullptr;
-    mcdp_plan* plan = new (std::nothrow) mcdp_plan();
+    std::unique_ptr<mcdp_plan> plan(new (std::nothrow) mcdp_plan(std::move(host)));
     if (!plan) return fail(MCDP_ERR_ARG, "out of host memory");
-    std::string err;
-    bool ok = false;
-    NvtxRange nvtx_compile("mcdp:plan compile");
-    try {
-        ok = compile_plan(*graph, *dists, plan->host, err);
-    } catch (const std::exception& e) {
-        err = e.what();
-    }
-    if (!ok) {
-        delete plan;
-        return fail(MCDP_ERR_INVALID, err);
-    }
     if (device == MCDP_DEVICE_NONE) {
         // validation / introspection only: every run call on this plan fails (there is no CPU path)
         plan->device = MCDP_DEVICE_NONE;
-        *out = plan;
+        *out = plan.release();
         return MCDP_OK;
     }
     // No CPU fallback: a runnable plan lives on a CUDA device or does not exist.
@@ -615,19 +613,16 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
     cudaError_t ce = cudaGetDeviceCount(&n_dev);
     if (ce != cudaSuccess || n_dev <= 0) {
         cudaGetLastError();
-        delete plan;
+        plan->device = MCDP_DEVICE_NONE;
         return fail(MCDP_ERR_CUDA, std::string("no usable CUDA device: ") + cudaGetErrorString(ce));
     }
     if (device < 0 || device >= n_dev) {
-        delete plan;
+        plan->device = MCDP_DEVICE_NONE;
         return fail(MCDP_ERR_ARG, "device ordinal out of range");
     }
     plan->device = device;
     DeviceGuard guard(device);
-    if (!guard.ok) {
-        delete plan;
-        return fail(MCDP_ERR_CUDA, "cudaSetDevice failed");
-    }
+    if (!guard.ok) return fail(MCDP_ERR_CUDA, "cudaSetDevice failed");
     cudaDeviceProp prop{};
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
         plan->sm_count = prop.multiProcessorCount;
@@ -652,12 +647,36 @@ int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* di
         make_log_table(lt.data());
         rc = upload(plan->d_log_tab, lt);
     }
-    if (rc) {
-        delete plan;
-        return rc;
-    }
-    *out = plan;
+    if (rc) return rc;
+    *out = plan.release();
     return MCDP_OK;
+}
+
+int32_t compile_host_plan(const mcdp_graph_desc* graph, const mcdp_dists_desc* dists, std::shared_ptr<HostPlan>* out) {
+    auto host = std::make_shared<HostPlan>();
+    std::string err;
+    bool ok = false;
+    NvtxRange nvtx_compile("mcdp:plan compile");
+    try {
+        ok = compile_plan(*graph, *dists, *host, err);
+    } catch (const std::exception& e) {
+        err = e.what();
+    }
+    if (!ok) return fail(MCDP_ERR_INVALID, err);
+    *out = std::move(host);
+    return MCDP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t mcdp_plan_create(const mcdp_graph_desc* graph, const mcdp_dists_desc* dists, int32_t device, mcdp_plan** out) {
+    if (!graph || !dists || !out) return fail(MCDP_ERR_ARG, "null argument");
+    *out = nullptr;
+    std::shared_ptr<HostPlan> host;
+    const int32_t rc = compile_host_plan(graph, dists, &host);
+    if (rc) return rc;
+    return plan_from_host(std::move(host), device, out);
 }
 
 void mcdp_plan_destroy(mcdp_plan* plan) { delete plan; }
@@ -840,13 +859,26 @@ int32_t run_attribution_locked(mcdp_plan* plan, const int32_t* d_seeds, int32_t 
     const HostPlan& h = plan->host;
     // scratch rows are recycled slots; samples are processed in chunks that bound the scratch
     const int64_t bytes_per_sample = int64_t(std::max(h.n_slots, 1)) * 8;
-    // scratch budget: what is already allocated, else half of the free HBM (deep DAGs keep many rows live)
+    // scratch budget: what is already allocated, else 60 % of the free HBM (deep DAGs keep many rows live)
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(4) << 30;
-    const int64_t budget = std::max<int64_t>(int64_t(plan->d_scratch.cap) * 8, int64_t(double(free_b) * 0.5));
+    const int64_t budget = std::max<int64_t>(int64_t(plan->d_scratch.cap) * 8, int64_t(double(free_b) * 0.6));
     int64_t chunk = std::max<int64_t>(64, budget / bytes_per_sample / 64 * 64);
     chunk = std::min<int64_t>(chunk, int64_t(1) << 22);
     chunk = std::min<int64_t>(chunk, round_up(std::max<int64_t>(n, 1), 64));
+    if (n > chunk) {
+        // several launches: whole waves of sample groups each (a launch of 0.9 waves idles a tenth of the machine for
+        // its whole duration), and equal sizes so the last launch is not a sliver
+        const LaunchShape s = choose_shape(plan, chunk, true, d_hist ? desc->n_bins : 0, attr);
+        const int64_t sm_warps = s.spl == 4 ? MCDP_QUAD_MAX_THREADS / 32 : 32;
+        const int64_t ctas_per_sm = std::max<int64_t>(1, sm_warps / (int64_t(s.wpg) * s.gpc));
+        const int64_t wave = int64_t(plan->sm_count) * ctas_per_sm * s.gpc * (s.spl == 4 ? kQuadSamples : 64);
+        if (chunk >= wave) {
+            chunk = chunk / wave * wave;
+            const int64_t launches = (n + chunk - 1) / chunk;
+            chunk = std::min(chunk, round_up((n + launches - 1) / launches, wave));
+        }
+    }
     MCDP_CUDA(plan->d_scratch.ensure(size_t(std::max(h.n_slots, 1)) * size_t(chunk)));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (int64_t off = 0; off < n; off += chunk) {
@@ -1119,3 +1151,5 @@ void mcdp_host_free(void* p) {
 }
 
 }  // extern "C"
+
+#include "mcdp_multi.inl"

@@ -45,10 +45,19 @@ constexpr int kQuadSamples = 128;  // samples per group
 // in one transposed pass -- lane -> (event, lane block) -- instead of running a five-stage shuffle butterfly and four
 // match.any rounds per event.  Layout per warp: [kStatSlots][32] {sum, sum of squares} f64 pairs, then
 // [kStatSlots][32] u32 histogram words (two bins per word, so up to kStatMaxBins bins).
+#ifndef MCDP_STAGE_SUMS
+#define MCDP_STAGE_SUMS 1  // 0: shuffle butterfly per event (flush_sums)
+#endif
+#ifndef MCDP_STAGE_HIST
+#define MCDP_STAGE_HIST 0  // 0: match.any aggregation per event; N >= 1: shared-memory counts, N replicas per warp (lane % N).
+                           // Measured on B200 (C3 / C5 / C4 reduced, ms): match.any 32.1 / 181 / 621, shared counts 33.2 / 203 /
+                           // 663 (four replicas 32.8 / 208 / 673): concentrated bins serialise the shared-memory reductions.
+#endif
 constexpr int kStatSlots = 4;
-constexpr int kStatMaxBins = 64;
+constexpr int kStatMaxBins = MCDP_STAGE_HIST ? 64 : 0;
+constexpr int kStatHistReplicas = MCDP_STAGE_HIST ? MCDP_STAGE_HIST : 1;
 constexpr int kStatSumBytes = kStatSlots * 32 * 16;
-constexpr int kStatHistBytes = kStatSlots * 32 * 4;
+constexpr int kStatHistBytes = kStatSlots * 32 * 4 * kStatHistReplicas;
 constexpr int kStatStride = kStatSumBytes + kStatHistBytes;
 __host__ __device__ inline size_t quad_stat_bytes(int n_warps) { return size_t(n_warps) * size_t(kStatStride); }
 
@@ -123,9 +132,16 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
         mbar_init(bar0 + 8, 1);
         mbar_fence_init();
     }
+    // one END unit (closes the open event of a warp whose level has run out of chunks)
+    __shared__ __align__(16) int4 s_end_unit[2];
+    if (threadIdx.x == 0) {
+        s_end_unit[0] = make_int4(0, 0, 0, 0);
+        s_end_unit[1] = make_int4(int(kKindEnd << 29), 0, int(kNoRow), 0);
+    }
+    const uint32_t end_buf = smem_u32(s_end_unit);
     // reduced modes: this warp's statistics staging area; the histogram words start at zero
     const uint32_t stat0 = smem_base + p.smem_stat_off + uint32_t(warp) * uint32_t(kStatStride);
-    const bool stage_hist = kReduced && p.hist != nullptr && p.n_bins <= kStatMaxBins;
+    const bool stage_hist = MCDP_STAGE_HIST != 0 && kReduced && p.hist != nullptr && p.n_bins <= kStatMaxBins;
     if constexpr (kReduced) {
 #pragma unroll
         for (int k = 0; k < kStatSlots; ++k)
@@ -230,6 +246,7 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
         // Sums: lane -> (slot e = lane & 3, lane block = lane >> 2): four parked {sum, sumsq} pairs each, then three
         // shuffle stages over the eight blocks.  The element order inside a block is rotated by e so that the eight
         // lanes of a quarter warp read eight different 16-byte bank groups.
+#if MCDP_STAGE_SUMS
         const int e = lane & 3, blk = lane >> 2;
         double as = 0.0, aq = 0.0;
 #pragma unroll
@@ -250,17 +267,25 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
             if (p.sum) atomicAdd(p.sum + my_ev, as);
             if (p.sumsq) atomicAdd(p.sumsq + my_ev, aq);
         }
+#endif
         if (stage_hist) {
             const int nb = p.n_bins;
 #pragma unroll
             for (int k = 0; k < kStatSlots; ++k) {
                 const uint32_t evk = __shfl_sync(0xFFFFFFFFu, my_ev, k);
                 if (k < n_staged) {
-                    const uint32_t wa = stat0 + uint32_t(kStatSumBytes) + uint32_t(k * 32 + lane) * 4u;
-                    uint32_t w;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(wa));
+                    const uint32_t wa = stat0 + uint32_t(kStatSumBytes) + uint32_t(k * kStatHistReplicas * 32 + lane) * 4u;
+                    uint32_t w = 0u;
+#pragma unroll
+                    for (int rep = 0; rep < kStatHistReplicas; ++rep) {
+                        uint32_t wr;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wr) : "r"(wa + uint32_t(rep) * 128u));
+                        w += wr;
+                    }
                     if (w) {
-                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa), "r"(0u) : "memory");
+#pragma unroll
+                        for (int rep = 0; rep < kStatHistReplicas; ++rep)
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(wa + uint32_t(rep) * 128u), "r"(0u) : "memory");
                         uint32_t* h = p.hist + size_t(evk) * nb + 2 * lane;
                         if (w & 0xFFFFu) atomicAdd(h, w & 0xFFFFu);
                         if (w >> 16) atomicAdd(h + 1, w >> 16);
@@ -292,21 +317,31 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
             {
                 const double sl = (x[0] + x[1]) + (x[2] + x[3]);
                 const double ql = (x[0] * x[0] + x[1] * x[1]) + (x[2] * x[2] + x[3] * x[3]);
+#if MCDP_STAGE_SUMS
                 asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(stat0 + uint32_t(n_staged * 32 + lane) * 16u), "d"(sl), "d"(ql)
                              : "memory");
+#else
+                flush_sums(p, ev, lane, sl, ql, 0u);
+#endif
             }
             if (p.late) {
                 // exceedance counts, 8 bits per threshold (at most 128 samples per warp): one REDUX, the atomics of the
-                // thresholds issued by different lanes of one instruction
+                // thresholds issued by different lanes of one instruction.  Straight-line over the lane's four samples;
+                // only a lane of the ragged last group (some of its columns are padding) takes the checked path.
                 uint32_t late_packed = 0u;
+                if (all_valid) {
 #pragma unroll
-                for (int t = 0; t < MCDP_MAX_THRESHOLDS; ++t) {
-                    if (t < p.n_thresholds) {
-                        const double th = p.thresholds[t];
+                    for (int t = 0; t < MCDP_MAX_THRESHOLDS; ++t) {
+                        if (t < p.n_thresholds) {
+                            const double th = p.thresholds[t];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (all_valid || valid[i]) add_if_gt(late_packed, x[i], th, 1u << (8 * t));
+                            for (int i = 0; i < 4; ++i) add_if_gt(late_packed, x[i], th, 1u << (8 * t));
+                        }
                     }
+                } else {
+                    for (int t = 0; t < p.n_thresholds; ++t)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) late_packed += uint32_t(valid[i] && x[i] > p.thresholds[t]) << (8 * t);
                 }
                 const uint32_t tot = __reduce_add_sync(0xFFFFFFFFu, late_packed);
                 if (lane < p.n_thresholds) {
@@ -321,10 +356,10 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
                 for (int i = 0; i < 4; ++i) b[i] = min(max(int(floor((x[i] - p.hist_lo) * p.hist_scale)), 0), nb - 1);
                 if (stage_hist) {
                     // counts into this warp's private 16-bit-pair histogram of the slot (shared-memory reductions)
-                    const uint32_t h0 = stat0 + uint32_t(kStatSumBytes) + uint32_t(n_staged) * 128u;
+                    const uint32_t h0 = stat0 + uint32_t(kStatSumBytes) + uint32_t(n_staged * kStatHistReplicas + (lane % kStatHistReplicas)) * 128u;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
-                        if (all_valid || valid[i]) atoms_add_u32(h0 + uint32_t(b[i] >> 1) * 4u, 1u << ((b[i] & 1) * 16));
+                        atoms_add_u32(h0 + uint32_t(b[i] >> 1) * 4u, valid[i] ? 1u << ((b[i] & 1) * 16) : 0u);
                 } else {
                     uint32_t* h = p.hist + size_t(ev) * nb;
 #pragma unroll
@@ -350,7 +385,10 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
             }
         }
     };
-    auto process = [&](uint32_t buf, int u0, uint32_t remaining) {
+    // An event stays open until the next header or END unit this warp meets -- the first unit of its next chunk, or
+    // the END unit it is handed when its level has no more chunks for it (below) -- so the close (finalize: stores,
+    // statistics) is inlined ONCE: two copies of it pushed the reduced kernels out of the instruction caches.
+    auto process = [&](uint32_t buf, int u0) {
 #pragma unroll kQuadUnitUnroll
         for (int u = u0; u < kChunkUnits; ++u) {
             const int4 q0 = lds128(buf + uint32_t(u) * 32u);
@@ -422,7 +460,6 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
                 apply(d);
             }
         }
-        if (open && remaining == 0u) finalize();
     };
 
     // ---- main loop ----
@@ -436,36 +473,43 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
         int c = grab(par);
         bool from_cursor = true;
         if (c < le) issue(c, buf_sel);
-        while (c < le) {
-            const uint32_t buf = ring0 + buf_sel * uint32_t(kChunkBytes);
-            mbar_wait(bar0 + buf_sel * 8u, (phase >> buf_sel) & 1u);
-            phase ^= 1u << buf_sel;
-            buf_sel ^= 1u;
-            const int4 h1 = lds128(buf + 16u);
-            const bool is_cont = (uint32_t(h1.x) >> 29) == kKindEnd;
-            const bool skip = DYN && from_cursor && is_cont;
-            const uint32_t remaining = skip ? 0u : uint32_t(h1.y);
-            from_cursor = remaining == 0u;
-            int cn;
-            if (from_cursor) {
-                cn = grab(par);
-            } else {
-                cn = c + 1;
-                if constexpr (!DYN) ++seq;
-            }
-            if (cn < le) issue(cn, buf_sel);
-            if (!skip) {
-                for (uint32_t uu = pf_unit; uu < uint32_t(kChunkUnits); uu += pf_step) {
-                    const uint32_t ua = buf + uu * 32u;
-                    uint32_t src, meta;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(src) : "r"(ua));
-                    asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(meta) : "r"(ua));
-                    if ((meta >> 29) < kKindEvent)
-                        prefetch_l2(reinterpret_cast<const char*>(p.realized) + (uint64_t(src) * p.ldb8 + pf_off));
+        for (;;) {
+            const bool tail = c >= le;  // no chunk left for this warp in this level: close what is open, through the END unit
+            if (tail && !open) break;
+            uint32_t buf = end_buf;
+            bool is_cont = false, skip = false;
+            int cn = c;
+            if (!tail) {
+                buf = ring0 + buf_sel * uint32_t(kChunkBytes);
+                mbar_wait(bar0 + buf_sel * 8u, (phase >> buf_sel) & 1u);
+                phase ^= 1u << buf_sel;
+                buf_sel ^= 1u;
+                const int4 h1 = lds128(buf + 16u);
+                is_cont = (uint32_t(h1.x) >> 29) == kKindEnd;
+                skip = DYN && from_cursor && is_cont;
+                const uint32_t remaining = skip ? 0u : uint32_t(h1.y);
+                from_cursor = remaining == 0u;
+                if (from_cursor) {
+                    cn = grab(par);
+                } else {
+                    cn = c + 1;
+                    if constexpr (!DYN) ++seq;
                 }
-                process(buf, is_cont ? 1 : 0, remaining);
+                if (cn < le) issue(cn, buf_sel);
+                if (!skip) {
+                    for (uint32_t uu = pf_unit; uu < uint32_t(kChunkUnits); uu += pf_step) {
+                        const uint32_t ua = buf + uu * 32u;
+                        uint32_t src, meta;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(src) : "r"(ua));
+                        asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(meta) : "r"(ua));
+                        if ((meta >> 29) < kKindEvent)
+                            prefetch_l2(reinterpret_cast<const char*>(p.realized) + (uint64_t(src) * p.ldb8 + pf_off));
+                    }
+                }
             }
+            if (!skip) process(buf, is_cont ? 1 : 0);
             __syncwarp();
+            if (tail) break;
             c = cn;
         }
         if constexpr (DYN) {

@@ -267,10 +267,12 @@ const T* arr_ptr(const py::array_t<T, py::array::c_style | py::array::forcecast>
 
 // ---- the propagator (reference Simulator, _core.cpp:162-362) ----
 class MonteCarloPropagator {
-    mcdp_plan* plan_ = nullptr;
+    // one compiled plan per device; every call shards its seeds over the set (a set of one is a plain plan)
+    mcdp_planset* set_ = nullptr;
+    std::vector<int32_t> devices_;
 
    public:
-    MonteCarloPropagator(const DagContext& ctx, const GenericDelayGenerator& gen, int device) {
+    MonteCarloPropagator(const DagContext& ctx, const GenericDelayGenerator& gen, int device, const py::object& devices) {
         // flatten the Python-side containers (the by-value conversion the reference also pays, _core.cpp:425-428)
         std::vector<double> earliest;
         earliest.reserve(ctx.events.size());
@@ -306,7 +308,7 @@ class MonteCarloPropagator {
         g.pred_src = src.data();
         g.pred_act = act.data();
         g.max_delay = ctx.max_delay;
-        create(g, gen, device);
+        create(g, gen, device, devices);
     }
 
     // additive: array ingest without per-object conversion
@@ -318,7 +320,7 @@ class MonteCarloPropagator {
                          py::array_t<int64_t, py::array::c_style | py::array::forcecast> prec_off,
                          py::array_t<int32_t, py::array::c_style | py::array::forcecast> pred_src,
                          py::array_t<int32_t, py::array::c_style | py::array::forcecast> pred_act, double max_delay,
-                         const GenericDelayGenerator& gen, int device) {
+                         const GenericDelayGenerator& gen, int device, const py::object& devices) {
         if (act_idx.size() != act_base.size() || act_idx.size() != act_type.size())
             throw std::runtime_error("from_arrays: activity arrays must have the same length");
         if (pred_src.size() != pred_act.size()) throw std::runtime_error("from_arrays: pred_src and pred_act differ in length");
@@ -338,36 +340,44 @@ class MonteCarloPropagator {
         g.pred_src = pred_src.data();
         g.pred_act = pred_act.data();
         g.max_delay = max_delay;
-        create(g, gen, device);
+        create(g, gen, device, devices);
     }
 
-    void create(const mcdp_graph_desc& g, const GenericDelayGenerator& gen, int device) {
+    void create(const mcdp_graph_desc& g, const GenericDelayGenerator& gen, int device, const py::object& devices) {
+        if (devices.is_none()) {
+            devices_ = {device};
+        } else {
+            for (const auto& d : devices) devices_.push_back(d.cast<int32_t>());
+            if (devices_.empty()) throw std::runtime_error("devices must name at least one CUDA device");
+        }
         FlatDists fd(gen);
         int32_t rc;
         {
             py::gil_scoped_release release;
-            rc = mcdp_plan_create(&g, &fd.desc, device, &plan_);
+            rc = mcdp_planset_create(&g, &fd.desc, devices_.data(), int32_t(devices_.size()), &set_);
         }
         if (rc != MCDP_OK) throw_last();
     }
 
-    ~MonteCarloPropagator() { mcdp_plan_destroy(plan_); }
+    ~MonteCarloPropagator() { mcdp_planset_destroy(set_); }
     MonteCarloPropagator(const MonteCarloPropagator&) = delete;
     MonteCarloPropagator& operator=(const MonteCarloPropagator&) = delete;
 
-    int node_count() const { return mcdp_plan_node_count(plan_); }
-    int activity_count() const { return mcdp_plan_activity_count(plan_); }
-    int level_count() const { return mcdp_plan_level_count(plan_); }
-    int device() const { return mcdp_plan_device(plan_); }
+    mcdp_plan* plan0() const { return mcdp_planset_plan(set_, 0); }
+    int node_count() const { return mcdp_plan_node_count(plan0()); }
+    int activity_count() const { return mcdp_plan_activity_count(plan0()); }
+    int level_count() const { return mcdp_plan_level_count(plan0()); }
+    int device() const { return mcdp_plan_device(plan0()); }
+    std::vector<int32_t> devices() const { return devices_; }
     void set_option(int option, int64_t value) {
-        if (mcdp_plan_set_option(plan_, option, value) != MCDP_OK) throw_last();
+        if (mcdp_planset_set_option(set_, option, value) != MCDP_OK) throw_last();
     }
 
     std::shared_ptr<SimBatch> run_batch(const std::vector<int>& seeds) {
         auto b = std::make_shared<SimBatch>(seeds.size(), size_t(node_count()), size_t(activity_count()));
         static_assert(sizeof(int) == sizeof(int32_t), "seeds are C ints");
-        int32_t rc = mcdp_run_many_host(plan_, reinterpret_cast<const int32_t*>(seeds.data()), int64_t(b->n), b->realized,
-                                        b->durations, b->cause);
+        int32_t rc = mcdp_run_many_host_multi(set_, reinterpret_cast<const int32_t*>(seeds.data()), int64_t(b->n), b->realized,
+                                              b->durations, b->cause);
         if (rc != MCDP_OK) throw_last();
         return b;
     }
@@ -401,7 +411,7 @@ class MonteCarloPropagator {
         int32_t rc;
         {
             py::gil_scoped_release release;
-            rc = mcdp_run_many_host(plan_, seeds.data(), n, r.mutable_data(), d.mutable_data(), c.mutable_data());
+            rc = mcdp_run_many_host_multi(set_, seeds.data(), n, r.mutable_data(), d.mutable_data(), c.mutable_data());
         }
         if (rc != MCDP_OK) throw_last();
         return py::make_tuple(r, d, c);
@@ -418,7 +428,7 @@ class MonteCarloPropagator {
         int32_t rc;
         {
             py::gil_scoped_release release;
-            rc = mcdp_run_injected_host(plan_, durations.data(), n, r.mutable_data(), c.mutable_data());
+            rc = mcdp_run_injected_host_multi(set_, durations.data(), n, r.mutable_data(), c.mutable_data());
         }
         if (rc != MCDP_OK) throw_last();
         return py::make_tuple(r, c);
@@ -444,7 +454,7 @@ class MonteCarloPropagator {
         int32_t rc;
         {
             py::gil_scoped_release release;
-            rc = mcdp_run_attribution_host(plan_, seeds.data(), n, &desc, sum.mutable_data(), sumsq.mutable_data(),
+            rc = mcdp_run_attribution_host_multi(set_, seeds.data(), n, &desc, sum.mutable_data(), sumsq.mutable_data(),
                                            late.size() ? late.mutable_data() : nullptr,
                                            hist.size() ? hist.mutable_data() : nullptr,
                                            cause_counts ? cause_act.mutable_data() : nullptr,
@@ -601,8 +611,10 @@ PYBIND11_MODULE(_core, m) {
             "Empirical relative: draw a factor in [0,inf), then multiply by the activity duration.");
 
     py::class_<MonteCarloPropagator>(m, "MonteCarloPropagator")
-        .def(py::init<const DagContext&, const GenericDelayGenerator&, int>(), py::arg("context"), py::arg("generator"),
-             py::arg("device") = 0, "Construct simulator with context and delay-generator (device: CUDA ordinal)")
+        .def(py::init<const DagContext&, const GenericDelayGenerator&, int, const py::object&>(), py::arg("context"),
+             py::arg("generator"), py::arg("device") = 0, py::arg("devices") = py::none(),
+             "Construct simulator with context and delay-generator (device: CUDA ordinal; devices: several ordinals -- "
+             "every call then shards its seeds over them)")
         .def_static(
             "from_arrays",
             [](py::array_t<double, py::array::c_style | py::array::forcecast> earliest,
@@ -613,17 +625,18 @@ PYBIND11_MODULE(_core, m) {
                py::array_t<int64_t, py::array::c_style | py::array::forcecast> prec_off,
                py::array_t<int32_t, py::array::c_style | py::array::forcecast> pred_src,
                py::array_t<int32_t, py::array::c_style | py::array::forcecast> pred_act, double max_delay,
-               const GenericDelayGenerator& gen, int device) {
+               const GenericDelayGenerator& gen, int device, const py::object& devices) {
                 return std::make_unique<MonteCarloPropagator>(earliest, act_idx, act_base, act_type, prec_target, prec_off,
-                                                              pred_src, pred_act, max_delay, gen, device);
+                                                              pred_src, pred_act, max_delay, gen, device, devices);
             },
             py::arg("earliest"), py::arg("act_idx"), py::arg("act_base"), py::arg("act_type"), py::arg("prec_target"),
             py::arg("prec_off"), py::arg("pred_src"), py::arg("pred_act"), py::arg("max_delay"), py::arg("generator"),
-            py::arg("device") = 0, "Construct from flat numpy arrays (no per-object conversion)")
+            py::arg("device") = 0, py::arg("devices") = py::none(), "Construct from flat numpy arrays (no per-object conversion)")
         .def("node_count", &MonteCarloPropagator::node_count, "Number of events")
         .def("activity_count", &MonteCarloPropagator::activity_count, "Number of links")
         .def("level_count", &MonteCarloPropagator::level_count, "Number of topological levels")
-        .def("device", &MonteCarloPropagator::device, "CUDA device ordinal")
+        .def("device", &MonteCarloPropagator::device, "CUDA device ordinal (the first one of a multi-device propagator)")
+        .def("devices", &MonteCarloPropagator::devices, "CUDA device ordinals the seeds of a call are sharded over")
         .def("set_option", &MonteCarloPropagator::set_option, py::arg("option"), py::arg("value"))
         .def("run", &MonteCarloPropagator::run, py::arg("seed"), "Run single sim")
         .def("run_many", &MonteCarloPropagator::run_many, py::arg("seeds"), "Run batch sims")

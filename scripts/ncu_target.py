@@ -7,6 +7,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from mc_dagprop_b200 import capi, synth
 from mc_dagprop_b200.flat import FlatDists
+if os.environ.get('MCDP_LIB'):  # scratch A/B builds
+    capi.LIB_PATH = os.path.abspath(os.environ['MCDP_LIB'])
 
 ap = argparse.ArgumentParser()
 ap.add_argument("workload"); ap.add_argument("mode", choices=["full", "reduced"]); ap.add_argument("n", type=int)

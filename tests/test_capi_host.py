@@ -220,3 +220,18 @@ def test_launch_shape_invariants(gen):
                     assert s["smem_bytes"] <= 227 * 1024
                     if c > 1:  # a cluster shares ONE group: quad kernel, one group per CTA, several warps, few groups
                         assert k == 4 and s["groups_per_cta"] == 1 and s["warps_per_group"] > 1 and s["grid"] <= 148
+
+
+def test_plan_set_compiles_once_for_host_only_devices_and_has_no_cpu_path():
+    """A plan set validates and compiles without a GPU (MCDP_DEVICE_NONE entries); every run call on it fails."""
+    dag, d = synth.random_dag(50, 3), synth.mixed_small_dists()
+    ps = capi.PlanSet(dag, d, [capi.DEVICE_NONE, capi.DEVICE_NONE])
+    assert len(ps) == 2 and ps.E == 50
+    for call in (lambda: ps.run_many_host(np.arange(4, dtype=np.int32)),
+                 lambda: ps.run_reduced_host(np.arange(4, dtype=np.int32), n_bins=4)):
+        with pytest.raises(RuntimeError, match="no CPU execution path"):
+            call()
+    bad = synth.random_dag(50, 3)
+    bad.max_delay = -1.0
+    with pytest.raises(RuntimeError, match="max_delay must be non-negative"):
+        capi.PlanSet(bad, d, [capi.DEVICE_NONE])

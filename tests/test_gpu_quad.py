@@ -271,10 +271,10 @@ def test_auto_rule_clusters_small_launches_only():
     dag, dists = synth.c3_network()
     plan = capi.Plan(dag, dists, device=0)
     small, full = plan.launch_shape(2048), plan.launch_shape(18944)
-    assert small["samples_per_lane"] == 4 and small["cluster"] == 8 and small["grid"] == 16 * 8
+    assert small["samples_per_lane"] == 4 and small["cluster"] == 4 and small["grid"] == 16 * 4
     assert full["cluster"] == 1 and full["grid"] == 148
     one = plan.launch_shape(1)
-    assert one["cluster"] == 8 and one["grid"] == 8
+    assert one["samples_per_lane"] == 4 and one["cluster"] == 8 and one["grid"] == 8
 
 
 @pytest.mark.parametrize("n_bins", [1, 7, 64, 65, 100])
