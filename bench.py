@@ -298,7 +298,9 @@ def timed_workload(cx: Ctx, wl: str, total: int, steps: int, warmup: int, varian
         s_late = torch.zeros((len(THRESHOLDS), E), dtype=torch.int64, device=cx.dev)
         s_hist = torch.zeros((E, N_BINS), dtype=torch.int32, device=cx.dev)
         stats = (s_sum, s_sq, s_late, s_hist)
-        n_launches, launch = 1, per_gpu  # the library chunks by its scratch budget (whole waves, equal sizes)
+        # one call per step; the library splits it into launches by its scratch budget (whole waves of sample groups)
+        launch = plan.reduced_chunk(per_gpu, N_BINS) if per_gpu else 0
+        n_launches = -(-per_gpu // launch) if launch else 0
 
         def step(i, timed, frac=1):
             for b in stats:
@@ -357,18 +359,23 @@ def timed_workload(cx: Ctx, wl: str, total: int, steps: int, warmup: int, varian
     value = total * A * steps / (total_ms * 1e-3)
     peak, peak_src = measured_peak_gbs()
     shape = plan.launch_shape(max(launch, 1), reduced, N_BINS if reduced else 0)
-    full = [(a.elapsed_time(b), m) for a, b, m in evs_launch if m == launch] or [(a.elapsed_time(b), m) for a, b, m in evs_launch]
-    avg_ms = float(np.mean([t for t, _ in full]))
-    achieved = full[0][1] * A * bpe / (avg_ms * 1e-3) / 1e9
+    if reduced:  # timed per call; a call is n_launches launches back to back
+        full = [(a.elapsed_time(b) / max(n_launches, 1), min(launch, m)) for a, b, m in evs_launch]
+        achieved = per_gpu * A * bpe / (float(np.mean([a.elapsed_time(b) for a, b, _ in evs_launch])) * 1e-3) / 1e9
+        avg_ms = float(np.mean([t for t, _ in full]))
+    else:
+        full = [(a.elapsed_time(b), m) for a, b, m in evs_launch if m == launch] or [(a.elapsed_time(b), m) for a, b, m in evs_launch]
+        avg_ms = float(np.mean([t for t, _ in full]))
+        achieved = full[0][1] * A * bpe / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "traffic_source": None, "peak_source": peak_src, "bytes_per_edge_sample": bpe,
                 "kernel": "mcdp::quad_sweep_kernel" if shape["samples_per_lane"] == 4 else "mcdp::chunk_sweep_kernel",
                 "avg_launch_ms": avg_ms, "samples_per_launch": full[0][1], "launches_timed": len(full),
                 "launch": {k: shape[k] for k in ("samples_per_lane", "warps_per_group", "groups_per_cta", "threads", "grid", "cluster")}}
     if reduced:
-        roofline["note"] = ("one API call per step; the library splits it into whole-wave launches by its scratch budget; "
-                            "avg_launch_ms is the call")
-    tail = [(a.elapsed_time(b), m) for a, b, m in evs_launch if m != launch]
+        roofline["note"] = (f"one API call per step, split by the library into {n_launches} launch(es) of <= {launch} samples "
+                            "(scratch budget, whole waves); avg_launch_ms = call time / launches")
+    tail = [] if reduced else [(a.elapsed_time(b), m) for a, b, m in evs_launch if m != launch]
     if tail:
         roofline["tail_launch"] = {"samples": tail[0][1], "avg_ms": float(np.mean([t for t, _ in tail]))}
     prof = os.path.join(ROOT, "profiles", f"traffic_{wl}.json")
@@ -385,7 +392,7 @@ def timed_workload(cx: Ctx, wl: str, total: int, steps: int, warmup: int, varian
             pass
     out = {"value": value, "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup,
            "config": main_config(wl, E, A, cx.world, total, per_gpu, launch, n_launches, reduced),
-           "roofline": roofline, "clocks": clocks, "gpu_launches": len(evs_launch)}
+           "roofline": roofline, "clocks": clocks, "gpu_launches": len(evs_launch) * (n_launches if reduced else 1)}
     if variant == "mt":
         out["config"]["workload"] = "c3-mt: the C3 DAG with gamma shapes 2.3 / 0.6 (Marsaglia-Tsang) + empirical-relative"
     if reduced and cx.dist is not None:

@@ -155,6 +155,11 @@ int64_t mcdp_plan_get_chunks(const mcdp_plan* plan, int32_t rows, int32_t dense,
  * thread-block cluster (1 = no cluster launch), 1 if the tables are staged in shared memory}. */
 int32_t mcdp_plan_launch_shape(const mcdp_plan* plan, int64_t n, int32_t reduced, int32_t n_bins, int64_t* out8);
 
+/* Samples per launch of a reduced / attribution call over n samples: such a call keeps realized[slot][sample] scratch
+ * rows (mcdp_plan_slot_count of them) and splits n into launches that fit its scratch budget -- what the plan has
+ * already allocated, else 60 % of the free device memory -- sized to whole waves of sample groups. */
+int64_t mcdp_plan_reduced_chunk(mcdp_plan* plan, int64_t n, int32_t n_bins, int32_t attribution);
+
 /* ---- device-buffer entry points (asynchronous on `stream`, a cudaStream_t passed as void*) ----
  * Seeds: d_seeds[n] (device) or, when d_seeds is NULL, the arithmetic run seed0, seed0+1, ... */
 

@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = (
     "mcdp_plan_level_count", "mcdp_plan_slot_count", "mcdp_plan_device", "mcdp_plan_get_order", "mcdp_plan_get_cumulative",
     "mcdp_run_full_device", "mcdp_run_injected_device", "mcdp_run_reduced_device", "mcdp_transpose_f64_device",
     "mcdp_transpose_i32_device", "mcdp_run_many_host", "mcdp_run_injected_host", "mcdp_run_reduced_host",
-    "mcdp_plan_get_chunks", "mcdp_plan_launch_shape", "mcdp_run_attribution_device", "mcdp_run_attribution_host", "mcdp_host_alloc", "mcdp_host_free",
+    "mcdp_plan_get_chunks", "mcdp_plan_launch_shape", "mcdp_plan_reduced_chunk", "mcdp_run_attribution_device", "mcdp_run_attribution_host", "mcdp_host_alloc", "mcdp_host_free",
     "mcdp_planset_create", "mcdp_planset_destroy", "mcdp_planset_size", "mcdp_planset_plan", "mcdp_planset_set_option",
     "mcdp_run_many_host_multi", "mcdp_run_injected_host_multi", "mcdp_run_reduced_host_multi", "mcdp_run_attribution_host_multi",
 )
@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
         L.mcdp_plan_get_chunks.argtypes = [vp, i32, i32, vp, i64, vp]
         L.mcdp_plan_get_chunks.restype = i64
         L.mcdp_plan_launch_shape.argtypes = [vp, i64, i32, i32, vp]
+        L.mcdp_plan_reduced_chunk.argtypes = [vp, i64, i32, i32]
+        L.mcdp_plan_reduced_chunk.restype = i64
         L.mcdp_run_full_device.argtypes = [vp, vp, i32, i64, vp, vp, vp, i64, vp]
         L.mcdp_run_injected_device.argtypes = [vp, vp, i64, vp, vp, i64, vp]
         L.mcdp_run_reduced_device.argtypes = [vp, vp, i32, i64, C.POINTER(StatsDesc), vp, vp, vp, vp, vp]
@@ -265,6 +267,10 @@ class Plan:
         _check(lib().mcdp_plan_launch_shape(self._h, int(n), int(bool(reduced)), int(n_bins), out.ctypes.data))
         keys = ("samples_per_lane", "warps_per_group", "groups_per_cta", "threads", "grid", "smem_bytes", "cluster", "smem_tables")
         return dict(zip(keys, out.tolist()))
+
+    def reduced_chunk(self, n: int, n_bins: int = 0, attribution: bool = False) -> int:
+        """Samples per launch a reduced call over n samples would use (scratch budget, whole waves)."""
+        return int(lib().mcdp_plan_reduced_chunk(self._h, int(n), int(n_bins), int(bool(attribution))))
 
     def set_option(self, option: int, value: int) -> None:
         _check(lib().mcdp_plan_set_option(self._h, option, int(value)))

@@ -407,6 +407,7 @@ int32_t launch_kernel(mcdp_plan* plan, K k, const SweepParams& p, const LaunchSh
 }
 
 int32_t ensure_chunk_stream(mcdp_plan* plan, bool reduced, bool dense, SweepParams& p);
+int64_t reduced_chunk(const mcdp_plan* plan, int64_t n, int n_bins, bool attr);
 
 // the launch-shape dependent fields of the parameter block
 void apply_shape(SweepParams& p, const LaunchShape& s) {
@@ -766,6 +767,13 @@ int64_t mcdp_plan_get_chunks(const mcdp_plan* plan, int32_t rows, int32_t dense,
     return int64_t(units.size() / size_t(kChunkUnits));
 }
 
+int64_t mcdp_plan_reduced_chunk(mcdp_plan* plan, int64_t n, int32_t n_bins, int32_t attribution) {
+    if (!plan || n < 0) return -1;
+    std::lock_guard<std::mutex> lock(plan->mu);
+    DeviceGuard guard(plan->device);
+    return reduced_chunk(plan, n, n_bins, attribution != 0);
+}
+
 int32_t mcdp_plan_launch_shape(const mcdp_plan* plan, int64_t n, int32_t reduced, int32_t n_bins, int64_t* out8) {
     if (!plan || !out8) return fail(MCDP_ERR_ARG, "null argument");
     if (n < 0) return fail(MCDP_ERR_ARG, "n must be non-negative");
@@ -838,6 +846,39 @@ int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t
 }  // extern "C"
 
 namespace {
+// Samples per launch of a reduced call over n samples.  The realized scratch uses recycled slot rows; the samples
+// are processed in chunks that bound it: what is already allocated, else 60 % of the free HBM (deep DAGs keep many
+// rows live).
+int64_t reduced_chunk(const mcdp_plan* plan, int64_t n, int n_bins, bool attr) {
+    const HostPlan& h = plan->host;
+    const int64_t bytes_per_sample = int64_t(std::max(h.n_slots, 1)) * 8;
+    size_t free_b = 0, total_b = 0;
+    if (plan->device < 0 || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+        cudaGetLastError();
+        free_b = size_t(160) << 30;
+    }
+    const int64_t budget = std::max<int64_t>(int64_t(plan->d_scratch.cap) * 8, int64_t(double(free_b) * 0.6));
+    int64_t chunk = std::max<int64_t>(64, budget / bytes_per_sample / 64 * 64);
+    chunk = std::min<int64_t>(chunk, int64_t(1) << 22);
+    chunk = std::min<int64_t>(chunk, round_up(std::max<int64_t>(n, 1), 64));
+    if (n > chunk) {
+        // several launches: whole waves of sample groups each (a launch of 0.9 waves idles a tenth of the machine for
+        // its whole duration), and equal sizes so the last launch is not a sliver
+        // (the wave of the kernel the launches will use: the quad kernel unless the plan is pinned to the pair kernel --
+        // asking the auto rule about the not yet aligned size would answer for a launch of 1.x waves)
+        const LaunchShape s = choose_shape(plan, chunk, true, n_bins, attr, plan->samples_per_lane == 2 ? 2 : 4);
+        const int64_t sm_warps = s.spl == 4 ? MCDP_QUAD_MAX_THREADS / 32 : 32;
+        const int64_t ctas_per_sm = std::max<int64_t>(1, sm_warps / (int64_t(s.wpg) * s.gpc));
+        const int64_t wave = int64_t(plan->sm_count) * ctas_per_sm * s.gpc * (s.spl == 4 ? kQuadSamples : 64);
+        if (chunk >= wave) {
+            chunk = chunk / wave * wave;
+            const int64_t launches = (n + chunk - 1) / chunk;
+            chunk = std::min(chunk, round_up((n + launches - 1) / launches, wave));
+        }
+    }
+    return chunk;
+}
+
 // plan->mu must be held by the caller (the device entry point and the host entry point both take it for the whole call)
 int32_t run_attribution_locked(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n,
                                const mcdp_stats_desc* desc, double* d_sum, double* d_sumsq,
@@ -857,28 +898,7 @@ int32_t run_attribution_locked(mcdp_plan* plan, const int32_t* d_seeds, int32_t 
     int32_t rc = ensure_reduced_stream(plan);
     if (rc) return rc;
     const HostPlan& h = plan->host;
-    // scratch rows are recycled slots; samples are processed in chunks that bound the scratch
-    const int64_t bytes_per_sample = int64_t(std::max(h.n_slots, 1)) * 8;
-    // scratch budget: what is already allocated, else 60 % of the free HBM (deep DAGs keep many rows live)
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(4) << 30;
-    const int64_t budget = std::max<int64_t>(int64_t(plan->d_scratch.cap) * 8, int64_t(double(free_b) * 0.6));
-    int64_t chunk = std::max<int64_t>(64, budget / bytes_per_sample / 64 * 64);
-    chunk = std::min<int64_t>(chunk, int64_t(1) << 22);
-    chunk = std::min<int64_t>(chunk, round_up(std::max<int64_t>(n, 1), 64));
-    if (n > chunk) {
-        // several launches: whole waves of sample groups each (a launch of 0.9 waves idles a tenth of the machine for
-        // its whole duration), and equal sizes so the last launch is not a sliver
-        const LaunchShape s = choose_shape(plan, chunk, true, d_hist ? desc->n_bins : 0, attr);
-        const int64_t sm_warps = s.spl == 4 ? MCDP_QUAD_MAX_THREADS / 32 : 32;
-        const int64_t ctas_per_sm = std::max<int64_t>(1, sm_warps / (int64_t(s.wpg) * s.gpc));
-        const int64_t wave = int64_t(plan->sm_count) * ctas_per_sm * s.gpc * (s.spl == 4 ? kQuadSamples : 64);
-        if (chunk >= wave) {
-            chunk = chunk / wave * wave;
-            const int64_t launches = (n + chunk - 1) / chunk;
-            chunk = std::min(chunk, round_up((n + launches - 1) / launches, wave));
-        }
-    }
+    const int64_t chunk = reduced_chunk(plan, n, d_hist ? desc->n_bins : 0, attr);
     MCDP_CUDA(plan->d_scratch.ensure(size_t(std::max(h.n_slots, 1)) * size_t(chunk)));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     for (int64_t off = 0; off < n; off += chunk) {

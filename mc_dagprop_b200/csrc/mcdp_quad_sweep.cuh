@@ -45,6 +45,11 @@ constexpr int kQuadSamples = 128;  // samples per group
 // in one transposed pass -- lane -> (event, lane block) -- instead of running a five-stage shuffle butterfly and four
 // match.any rounds per event.  Layout per warp: [kStatSlots][32] {sum, sum of squares} f64 pairs, then
 // [kStatSlots][32] u32 histogram words (two bins per word, so up to kStatMaxBins bins).
+#ifndef MCDP_RELAX_LITERAL
+#define MCDP_RELAX_LITERAL 1  // 1: the reference's literal clamp-then-compare form of the recurrence; 0: relax() of
+                              // mcdp_sweep.cuh (two compares, no clamp).  Measured on one B200, C3 / C3-MT / C2 full, ms:
+                              // literal 25.57 / 29.3 / 33.5, relax() 26.20 / 30.1 / 34.4 -- fewer instructions, worse schedule.
+#endif
 #ifndef MCDP_STAGE_SUMS
 #define MCDP_STAGE_SUMS 1  // 0: shuffle butterfly per event (flush_sums)
 #endif
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
     // ---- the running event of this warp ----
     bool open = false;
     uint32_t row = 0u;
-    double lat[4] = {0.0, 0.0, 0.0, 0.0}, ub = 0.0;
+    double lat[4] = {0.0, 0.0, 0.0, 0.0}, ub = 0.0;  // lat: the running UNCLAMPED arrival of the open event (see relax)
     int cause[4] = {-1, -1, -1, -1};
     D4 nrs{0.0, 0.0, 0.0, 0.0};
     uint32_t ev = 0u;
@@ -434,11 +439,15 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
                 const double rsv[4] = {rs.x, rs.y, rs.z, rs.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+#if MCDP_RELAX_LITERAL
                     const double t = ref_min(__dadd_rn(rsv[i], d[i]), ub);
                     if (t >= lat[i]) {
                         lat[i] = t;
                         cause[i] = src_event;
                     }
+#else
+                    relax(__dadd_rn(rsv[i], d[i]), ub, lat[i], cause[i], src_event);
+#endif
                 }
             };
             if constexpr (MODE == kModeInjected) {

@@ -106,6 +106,25 @@ __device__ __forceinline__ void flush_sums(const P& p, uint32_t ev, int lane, do
 // std::min(a, b) of the reference build: (b < a) ? b : a  -- NOT fmin (NaN / signed-zero differ).
 __device__ __forceinline__ double ref_min(double a, double b) { return (b < a) ? b : a; }
 
+// One relaxation of the recurrence (_core.cpp:341-346) without materialising the clamp.  The reference keeps
+//     lat <- t  if  t >= lat,   t = std::min(a, ub),   a = realized[src] + duration,
+// and closes the event with realized = std::min(lat, ub).  Here `run` holds the UNCLAMPED arrival of the entry that
+// last won, with the invariant lat == std::min(run, ub) (bit for bit):
+//   * a >= ub:  t is ub (or a itself when they compare equal) and t >= lat always holds because lat <= ub: the entry
+//               wins, and std::min(a, ub) reproduces t, signed zeros included;
+//   * a <  ub:  t is a; lat is run when run <= ub (the test is a >= run) and ub otherwise (a >= ub fails, and so does
+//               a >= run since a < ub < run);
+//   * a NaN:    both compares fail, as t >= lat does in the reference (t is NaN); a NaN `run` or ub can only come from
+//               a NaN `earliest`, and then nothing ever wins in either formulation.
+// Two compares (the second folds the first in: DSETP.GE.OR) and predicated moves instead of compare + two selects for
+// the clamp and compare + three selects for the update.  Bit-exact parity incl. NaN / inf / signed zeros is pinned by
+// tests/test_gpu_parity.py::test_injected_special_values and the pair kernel, which keeps the literal form.
+__device__ __forceinline__ void relax(double a, double ub, double& run, int& cause, int src) {
+    const bool take = (a >= run) | (a >= ub);
+    run = take ? a : run;
+    cause = take ? src : cause;
+}
+
 // out[c][r] = in[r][c]  (in: rows x cols with row stride in_ld; out: cols x rows, stride out_ld).
 // 1-D grid of 32x32 tiles (either extent can exceed the 65535 limit of grid.y).
 template <typename T>

@@ -55,7 +55,8 @@ def test_reduced_statistics_equal_one_device(n):
         assert np.array_equal(st.late, ref.late) and np.array_equal(st.hist, ref.hist), devs
         assert np.array_equal(act, ref_act) and np.array_equal(none, ref_none), devs
         st2 = ps.run_reduced_host(seeds, thresholds=th, n_bins=24, hist_range=(0.0, 60.0))  # repeatable, no stale state
-        assert np.array_equal(st2.hist, ref.hist) and np.array_equal(st2.sum, st.sum)
+        assert np.array_equal(st2.hist, ref.hist) and np.array_equal(st2.late, ref.late)
+        np.testing.assert_allclose(st2.sum, st.sum, rtol=1e-12, atol=1e-9)  # (f64 atomics: order varies run to run)
         only_hist = ps.run_reduced_host(seeds, n_bins=24, hist_range=(0.0, 60.0))
         assert only_hist.late.shape == (0, ps.E) and np.array_equal(only_hist.hist, ref.hist)
 
@@ -105,8 +106,8 @@ def test_drop_in_propagator_over_several_devices():
     for x, y in zip(a, b):
         assert np.array_equal(x.realized, y.realized) and np.array_equal(x.durations, y.durations)
         assert np.array_equal(x.cause_event, y.cause_event)
-    ra, rb = one.run_many_reduced(np.asarray(seeds, np.int32), [1.0], 8, 0.0, 50.0, True), \\
-        many.run_many_reduced(np.asarray(seeds, np.int32), [1.0], 8, 0.0, 50.0, True)
+    ra = one.run_many_reduced(np.asarray(seeds, np.int32), [1.0], 8, 0.0, 50.0, True)
+    rb = many.run_many_reduced(np.asarray(seeds, np.int32), [1.0], 8, 0.0, 50.0, True)
     for k in ("late", "hist", "cause_activity", "cause_none"):
         assert np.array_equal(ra[k], rb[k]), k
     np.testing.assert_allclose(ra["sum"], rb["sum"], rtol=1e-12, atol=1e-9)
