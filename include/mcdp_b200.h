@@ -234,6 +234,43 @@ int32_t mcdp_run_attribution_host_multi(mcdp_planset* set, const int32_t* seeds,
                                         double* sum, double* sumsq, unsigned long long* late, uint32_t* hist,
                                         unsigned long long* cause_act, unsigned long long* cause_none);
 
+/* ---- analytic (PMF) propagation (additive) ----
+ * Replaces the pure-numpy engine of the reference: DiscretePMF.convolve / maximum (analytic/_pmf.py:107-148),
+ * AnalyticPropagator.run (analytic/_propagator.py:89-148) and its bound handling _convert_to_simulated_event
+ * (:158-265).  All times are integer seconds on the grid of `step`; PMF i has its first value at pmf_start[i] and the
+ * probabilities pmf_probs[pmf_off[i] .. pmf_off[i+1]) at spacing `step`. */
+typedef struct {
+    int32_t n_events;
+    const int64_t* lower;   /* [E] int(round(earliest))                                   _propagator.py:150-156 */
+    const int64_t* upper;   /* [E] int(round(min(latest, earliest + max_delay)))                                 */
+    const int64_t* origin;  /* [E] value of an event without predecessors: round(earliest / step) * step  :104-106 */
+    int64_t step;
+    int32_t n_prec_entries; /* precedence list as in mcdp_graph_desc; pred_pmf[k] = PMF index of that edge */
+    const int32_t* prec_target;
+    const int64_t* prec_off;
+    const int32_t* pred_src;
+    const int32_t* pred_pmf;
+    int32_t n_pmfs;
+    const int64_t* pmf_start;
+    const int64_t* pmf_off; /* [n_pmfs + 1] */
+    const double* pmf_probs;
+    int32_t underflow_rule, overflow_rule; /* 1 truncate, 2 remove, 3 redistribute (analytic/_context.py:42-66) */
+} mcdp_analytic_desc;
+
+/* Bins the result arrays must hold; out_off (may be NULL) receives the [E + 1] slot offsets of the events. */
+int64_t mcdp_analytic_out_capacity(const mcdp_analytic_desc* desc, int64_t* out_off);
+/* One launch per topological level, one CTA per event.  Event e's PMF: first value out_start[e], out_len[e] bins at
+ * out_probs[out_off[e] ..]; underflow[e] / overflow[e] as SimulatedEvent reports them.  Failures of the reference's
+ * checks (cycle, no bound bin to truncate onto, empty PMF) return MCDP_ERR_INVALID with its message. */
+int32_t mcdp_analytic_run(const mcdp_analytic_desc* desc, int32_t device, int64_t* out_start, int32_t* out_len, int64_t* out_off,
+                          double* out_probs, int64_t out_cap, double* underflow, double* overflow);
+/* A single PMF operation on the device: op 0 = convolve(a, b), 1 = maximum(a, b), 2 = clip a to [min_value, max_value]
+ * with the flow rules (b unused). */
+int32_t mcdp_pmf_op(int32_t op, int32_t device, int64_t step, int64_t a_start, int32_t a_len, const double* a_probs, int64_t b_start,
+                    int32_t b_len, const double* b_probs, int64_t min_value, int64_t max_value, int32_t underflow_rule,
+                    int32_t overflow_rule, int64_t* out_start, int32_t* out_len, double* out_probs, int64_t out_cap,
+                    double* out_underflow, double* out_overflow);
+
 void* mcdp_host_alloc(size_t bytes); /* pinned host memory, NULL on failure */
 void mcdp_host_free(void* p);
 

@@ -2,8 +2,7 @@
 
 ``from mc_dagprop import Simulator, DagContext, ...`` keeps working for code written against
 WonJayne/mc_dagprop (reference ``src/mc_dagprop/__init__.py``); every name resolves to
-``mc_dagprop_b200``.  The analytic (PMF) propagator of the reference is a different algorithm and
-is not part of this package (out of scope).
+``mc_dagprop_b200`` -- the Monte-Carlo classes and the analytic (PMF) propagator alike.
 """
 from mc_dagprop_b200 import __version__
 from mc_dagprop_b200.monte_carlo import (
@@ -17,6 +16,16 @@ from mc_dagprop_b200.monte_carlo import (
     Simulator,
 )
 
+from mc_dagprop_b200.analytic import (  # noqa: E402
+    AnalyticContext,
+    AnalyticPropagator,
+    DiscretePMF,
+    OverflowRule,
+    SimulatedEvent,
+    UnderflowRule,
+    create_analytic_propagator,
+)
+
 __all__ = [
     "GenericDelayGenerator",
     "DagContext",
@@ -26,5 +35,12 @@ __all__ = [
     "Simulator",
     "MonteCarloPropagator",
     "EventTimestamp",
+    "DiscretePMF",
+    "SimulatedEvent",
+    "UnderflowRule",
+    "OverflowRule",
+    "AnalyticContext",
+    "AnalyticPropagator",
+    "create_analytic_propagator",
     "__version__",
 ]

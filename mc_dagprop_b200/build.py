@@ -43,7 +43,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     if force or _newer(LIB, deps):
         cmd = [NVCC, "-O3", "-std=c++17", *ARCH_FLAGS, "-lineinfo", "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-O3,-Wall",
                "-shared", "-cudart", "static", "-o", LIB, *os.environ.get("MCDP_NVCC_EXTRA", "").split(),
-               os.path.join(CSRC, "mcdp_capi.cu"), os.path.join(CSRC, "mcdp_plan.cpp")]
+               os.path.join(CSRC, "mcdp_capi.cu"), os.path.join(CSRC, "mcdp_analytic.cu"), os.path.join(CSRC, "mcdp_plan.cpp")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)

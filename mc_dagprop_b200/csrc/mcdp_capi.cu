@@ -34,6 +34,13 @@ int32_t fail(int32_t code, const std::string& msg) {
     return code;
 }
 
+}  // namespace
+
+// the same thread-local message for the other translation units of the library (mcdp_analytic.cu)
+int32_t mcdp_set_error(int32_t code, const std::string& msg) { return fail(code, msg); }
+
+namespace {
+
 #define MCDP_CUDA(expr)                                                                             \
     do {                                                                                            \
         cudaError_t _e = (expr);                                                                    \

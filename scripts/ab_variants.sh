@@ -10,7 +10,7 @@ for v in "$@"; do
   name=${v%%:*}; flags=${v#*:}
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -ccbin ${MCDP_HOST_CXX:-/usr/bin/g++} \
        -Xcompiler -fPIC,-O3 -shared -cudart static ${flags//,/ } -o scratch_libs/lib$name.so \
-       mc_dagprop_b200/csrc/mcdp_capi.cu mc_dagprop_b200/csrc/mcdp_plan.cpp &
+       mc_dagprop_b200/csrc/mcdp_capi.cu mc_dagprop_b200/csrc/mcdp_analytic.cu mc_dagprop_b200/csrc/mcdp_plan.cpp &
 done
 wait
 ls -la scratch_libs

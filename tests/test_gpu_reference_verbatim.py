@@ -1,5 +1,5 @@
-"""The reference's own Monte-Carlo tests, run UNMODIFIED against the drop-in package (SURVEY.md section 4,
-implication 1).
+"""The reference's own test suite, run UNMODIFIED against the drop-in package (SURVEY.md section 4,
+implication 1): the Monte-Carlo tests and, with the analytic engine on the GPU, the whole of ``test/``.
 
 ``oracle/Makefile`` copies ``/root/reference/test`` and ``/root/reference/demo`` into
 ``oracle/_ref/reference_tests`` (git-ignored, travels to the GPU box, which has no ``/root/reference``).  Here the
@@ -10,7 +10,9 @@ resolves ``mc_dagprop`` to this repository's alias package:
   ``test_naming_conventions.py`` except the three known-answer tests that pin the reference's Xoshiro256++ stream
   (``test_simulator.py:139-172``) -- a different stream by design;
 * reference-compatible stream (``MCDP_OPT_RNG_STREAM = 1``, switched on by a conftest written next to the copies):
-  all of them, the three known-answer tests included.
+  all of them, the three known-answer tests included;
+* the whole reference suite -- all eight files of ``test/`` with ``demo/`` beside them (analytic propagator, PMF
+  class, distributions, MC-vs-analytic parity suite, analytic demo) -- under the default generator.
 """
 import os
 import shutil
@@ -81,3 +83,17 @@ def test_reference_mc_tests_pass_unmodified_reference_stream(tmp_path):
     assert res.returncode == 0, res.stdout[-4000:] + res.stderr[-2000:]
     assert "passed" in _summary(res.stdout) and "failed" not in _summary(res.stdout)
     assert "deselected" not in _summary(res.stdout)
+
+
+def test_whole_reference_suite_passes_unmodified(tmp_path):
+    """All of the reference's test/ (61 tests) against the drop-in package: Monte-Carlo and analytic engines on the
+    GPU, the reference's own conftest (it puts the tree's root on sys.path so that ``import demo`` works)."""
+    root = tmp_path / "reference_tree"
+    shutil.copytree(os.path.dirname(REF_TESTS), root)  # test/ and demo/
+    env = dict(os.environ)
+    env["PYTHONPATH"] = ROOT + os.pathsep + env.get("PYTHONPATH", "")
+    cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "test", *[a for k in XOSHIRO_KAT for a in ("--deselect", "test/" + k)]]
+    res = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=1800)
+    assert res.returncode == 0, res.stdout[-6000:] + res.stderr[-2000:]
+    summary = _summary(res.stdout)
+    assert "58 passed" in summary and "3 deselected" in summary and "failed" not in summary, summary
