@@ -52,9 +52,7 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                 r.p[1] = p1;
                 r.p[2] = std::isinf(p1) ? 1.0 : -std::expm1(-p1 / p0);  // P(x <= max_scale)
                 if (r.p[2] < 0x1p-10) r.flags |= 2;
-                // contract v2: a 32-bit uniform (QUAD block) when the truncation keeps the variate within 16 means,
-                // where 2^-32 steps of u are far below the law's own scale; the open tail keeps 64 bits
-                if (p1 <= kQuadExpMaxRatio * p0) r.flags |= 16;
+                r.p[3] = std::isinf(p1) ? 0.0 : std::exp(-p1 / p0);  // 1 - F, for the refined tail (contract v2)
                 r.p[7] = 1.0 / p0;  // rate, as ExponentialDist's constructor computes it (_core.cpp:81)
                 break;
             }

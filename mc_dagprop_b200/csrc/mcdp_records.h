@@ -46,10 +46,13 @@ struct alignas(16) PredRec {
 };
 static_assert(sizeof(PredRec) == 32, "PredRec must be 32 bytes");
 
-// Generator contract v2, width rule (restated by the oracle): which draws take one 32-bit word of a QUAD block
+// Generator contract v2, width rules (restated by the oracle): which draws take one 32-bit word of a QUAD block
 // instead of 64 bits of a PAIR block
 constexpr uint32_t kQuadTableMaxLen = 4096u;  // empirical tables of at most this many entries (then guide_log2 <= 16)
-constexpr double kQuadExpMaxRatio = 16.0;     // exponentials with max_scale <= this many means
+// Exponentials always start from one 32-bit word w: u = (w + 1/2) 2^-32.  In the top 2^-20 of the unit interval
+// (w >= kExpTailWord), where the inverse CDF is steep, a second word w' refines the same draw to 64 bits:
+// 1 - u = ((2^32 - w) - (w' + 1/2) 2^-32) 2^-32 -- the tail keeps the resolution a 64-bit draw would have.
+constexpr uint32_t kExpTailWord = 0xFFFFF000u;
 
 constexpr uint32_t kKindNone = 5u;   // precedence entry without a distribution (duration = base)
 constexpr uint32_t kKindEvent = 6u;  // chunk stream: event header unit
@@ -94,7 +97,7 @@ static_assert(sizeof(ChunkUnit) == 32, "ChunkUnit must be 32 bytes");
 // Distribution parameters, one per activity_type.
 //   CONSTANT     p0 = factor
 //   EXPONENTIAL  p0 = lambda (mean), p1 = max_scale, p2 = F = 1 - exp(-max_scale/lambda);
-//                flags bit1 = F < 2^-10 (series instead of log), bit4 = max_scale <= 16 lambda (32-bit uniform)
+//                p3 = 1 - F = exp(-max_scale/lambda); flags bit1 = F < 2^-10 (series instead of log, no tail refinement)
 //   GAMMA        p0 = shape, p1 = scale, p2 = max_scale, p3 = d = shape' - 1/3,
 //                p4 = c = 1/sqrt(9 d), p5 = 1/shape, p6 = d * scale; flags bit0 = shape < 1 (boost)
 //   EMP_ABS/REL  tab_len entries in the pool block at tab_off (see PredRec)
@@ -103,8 +106,7 @@ struct alignas(16) DistRec {
     int32_t tab_len;
     int32_t tab_off;
     int32_t guide_log2;
-    int32_t flags;      // bit0 gamma shape < 1, bit1 exponential series, bit2 table needs the scan loop, bit4 exponential
-                        // drawn from a 32-bit uniform,
+    int32_t flags;      // bit0 gamma shape < 1, bit1 exponential series, bit2 table needs the scan loop,
                         // bit3 gamma with 2*shape in {1..6, 8} (exact transformation: pad0 = floor(shape), pad1 = half term)
     int32_t pad0, pad1, pad2;
     double p[8];

@@ -8,10 +8,9 @@
 //
 //   key     = (stream_key, 'MCDP')                     -- round keys precomputed, read as constant operands
 //   QUAD    ctr = (seed >> 2, act, j, 'QUAD')          -- one block serves seeds {4k .. 4k+3}: 32 bits each (word seed & 3):
-//                                                         empirical tables of <= 4096 entries, exponentials with
-//                                                         max_scale <= 16 lambda, gamma shape 1
-//   PAIR    ctr = (seed >> 1, act, j, 'PAIR')          -- one block serves seeds {2k, 2k+1}: 64 bits each (the other
-//                                                         tables and exponentials)
+//                                                         empirical tables of <= 4096 entries, exponentials (j = 1
+//                                                         refines a draw that falls into the top 2^-20), gamma shape 1
+//   PAIR    ctr = (seed >> 1, act, j, 'PAIR')          -- one block serves seeds {2k, 2k+1}: 64 bits each (larger tables)
 //   SOLO    ctr = (seed,      act, t, 'SOLO')          -- gamma attempt t >= 1: 4 x 32 bits
 //   GAM0    ctr = (seed >> 1, act, 0, 'GAM0')          -- gamma attempt 0 of the seed pair: one Box-Muller pair
 //                                                         (cos branch: even seed, sin branch: odd seed) + two accept words
@@ -102,6 +101,17 @@ __device__ __forceinline__ void draw32x2(uint32_t seed_a, uint32_t seed_b, uint3
     }
 }
 
+// The refined tail of an exponential draw (contract v2): w >= kExpTailWord is the sample's first word; the second word
+// v is the seed's word of QUAD block j = 1; 1 - u = ((2^32 - w) - (v + 1/2) 2^-32) 2^-32 exactly and
+// x = -lambda ln((1 - F) + F (1 - u)).  One sample in 2^20 comes here: kept out of line so that its Philox block and
+// log do not weigh on the register allocation of the sweep loop.
+__device__ __forceinline__ double exp_tail(double lam, double F, double one_minus_F, uint32_t w, uint32_t seed, uint32_t act,
+                                        const PhiloxKeys* key0, uint32_t log_tab) {
+    const uint32_t v = philox_word(philox4x32_10(seed >> 2, act, 1u, kTagQuad, *key0), seed & 3u);
+    const double one_minus_u = (double(0u - w) - uniform32(v)) * 0x1p-32;
+    return -lam * log_pos(fma(F, one_minus_u, one_minus_F), log_tab);
+}
+
 // Table / distribution-record access.  SMEM: the staged copy in shared memory, addressed by 32-bit
 // shared-window addresses and explicit ld.shared (no generic pointers: the kernel keeps ONE base
 // register instead of re-deriving the window base at every use); else global memory through L1/L2.
@@ -139,6 +149,15 @@ struct DistView {
 static_assert(offsetof(DistRec, flags) == 16 && offsetof(DistRec, pad0) == 20 && offsetof(DistRec, pad1) == 24 &&
                   offsetof(DistRec, p) == 32,
               "DistView offsets follow DistRec");
+
+// exp_tail with the parameters read from the distribution record inside the out-of-line function (fewer live
+// registers at the call site)
+template <bool SMEM>
+__device__ __noinline__ double exp_tail_rec(typename Mem<SMEM>::ptr rec, uint32_t w, uint32_t seed, uint32_t act,
+                                            const PhiloxKeys* key0, uint32_t log_tab) {
+    const DistView<SMEM> d{rec};
+    return exp_tail(d.p(0), d.p(2), d.p(3), w, seed, act, key0, log_tab);
+}
 
 // Inverse-CDF lookup with std::lower_bound semantics (first cp[i] >= u; libstdc++
 // random.tcc:2709-2713): the guide table (four buckets per entry) gives the first candidate, one
@@ -428,19 +447,35 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, t
         eb = __dmul_rn(xb, base);
         return;
     }
-    // One uniform per sample.  Width by the contract's rule: 32 bits from a QUAD block for tables of <= 4096 entries and
-    // exponentials with max_scale <= 16 lambda (flags bit4), else 64 bits from a PAIR block.
-    const bool table = kind != MCDP_DIST_EXPONENTIAL;
-    bool narrow;
-    if (table) {
-        narrow = (meta & 0x7FFFFFu) <= kQuadTableMaxLen;
-    } else {
+    if (kind == MCDP_DIST_EXPONENTIAL) {
+        // inverse CDF of the exponential truncated to [0, max_scale]: the law of the reference's rejection loop
+        // (_core.cpp:83-89), without the loop.  One 32-bit word per sample, refined by a second one in the far tail.
         const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
-        narrow = d.flags() & 16;
+        uint32_t wa, wb;
+        draw32x2(seed_a, seed_b, 0u, 0u, act, kTagQuad, key0, wa, wb);
+        const double lam = d.p(0), mx = d.p(1), F = d.p(2);
+        const bool tiny = d.flags() & 2;  // F < 2^-10: series keeps the relative accuracy
+        double xa, xb;
+        if (tiny) {
+            xa = lam * neg_log1m(uniform32(wa) * F, true, log_tab);
+            xb = lam * neg_log1m(uniform32(wb) * F, true, log_tab);
+        } else {
+            xa = lam * neg_log1m(uniform32(wa) * F, false, log_tab);
+            xb = lam * neg_log1m(uniform32(wb) * F, false, log_tab);
+            if (wa >= kExpTailWord) xa = exp_tail_rec<SMEM>(d.base, wa, seed_a, act, &key0, log_tab);
+            if (wb >= kExpTailWord) xb = exp_tail_rec<SMEM>(d.base, wb, seed_b, act, &key0, log_tab);
+        }
+        xa = xa > mx ? mx : xa;
+        xb = xb > mx ? mx : xb;
+        ea = __dmul_rn(xa, base);
+        eb = __dmul_rn(xb, base);
+        return;
     }
+    // One uniform per sample for the table lookup: 32 bits from a QUAD block for tables of <= 4096 entries, else 64
+    // bits from a PAIR block.
     uint32_t hi_a, hi_b;
     double ua, ub;
-    if (narrow) {
+    if ((meta & 0x7FFFFFu) <= kQuadTableMaxLen) {
         draw32x2(seed_a, seed_b, 0u, 0u, act, kTagQuad, key0, hi_a, hi_b);
         ua = uniform32(hi_a);
         ub = uniform32(hi_b);
@@ -463,25 +498,6 @@ __device__ __forceinline__ void sample_extra2(uint32_t meta, uint32_t tab_off, t
         }
         ua = uniform52(lo_a, hi_a);
         ub = uniform52(lo_b, hi_b);
-    }
-    if (kind == MCDP_DIST_EXPONENTIAL) {
-        // inverse CDF of the exponential truncated to [0, max_scale]: the law of the
-        // reference's rejection loop (_core.cpp:83-89), without the loop.
-        const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
-        const double lam = d.p(0), mx = d.p(1), F = d.p(2);
-        double xa, xb;
-        if (d.flags() & 2) {  // F < 2^-10: series keeps the relative accuracy (both samples in one block)
-            xa = lam * neg_log1m(ua * F, true, log_tab);
-            xb = lam * neg_log1m(ub * F, true, log_tab);
-        } else {
-            xa = lam * neg_log1m(ua * F, false, log_tab);
-            xb = lam * neg_log1m(ub * F, false, log_tab);
-        }
-        xa = xa > mx ? mx : xa;
-        xb = xb > mx ? mx : xb;
-        ea = __dmul_rn(xa, base);
-        eb = __dmul_rn(xb, base);
-        return;
     }
     // empirical tables: pool block = [guide u32 x 2^g][cp f64 x len][values f64 x len]; the record
     // carries the byte offsets of guide (tab_off) and cp (dist)

@@ -272,33 +272,30 @@ __device__ __forceinline__ void sample_extra4(uint32_t meta, uint32_t tab_off, t
         for (int i = 0; i < 4; ++i) e[i] = __dmul_rn(x[i], base);
         return;
     }
-    // One uniform per sample: 32 bits from ONE QUAD block for the whole lane-quad when the contract's width rule
-    // allows (tables of <= 4096 entries, exponentials with flags bit4), else 64 bits from two PAIR blocks.
     uint32_t hi[4];
     double u[4];
     const uint32_t j0[4] = {0u, 0u, 0u, 0u};
     if (kind == MCDP_DIST_EXPONENTIAL) {
-        // inverse CDF of the exponential truncated to [0, max_scale] (see sample_extra2; _core.cpp:83-89)
+        // inverse CDF of the exponential truncated to [0, max_scale] (see sample_extra2; _core.cpp:83-89): ONE QUAD
+        // block for the lane's four samples; a sample in the top 2^-20 is refined out of line (exp_tail)
         const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
-        const int flags = d.flags();
-        if (flags & 16) {
-            draw32x4(sd, true, j0, act, kTagQuad, key0, hi);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) u[i] = uniform32(hi[i]);
-        } else {
-            uint32_t lo[4];
-            draw64x4(sd, true, j0, act, kTagPair, key0, lo, hi);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) u[i] = uniform52(lo[i], hi[i]);
-        }
+        draw32x4(sd, true, j0, act, kTagQuad, key0, hi);
         const double lam = d.p(0), mx = d.p(1), F = d.p(2);
         double x[4];
-        if (flags & 2) {
+        if (d.flags() & 2) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = lam * neg_log1m(u[i] * F, true, log_tab);
+            for (int i = 0; i < 4; ++i) x[i] = lam * neg_log1m(uniform32(hi[i]) * F, true, log_tab);
         } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = lam * neg_log1m(u[i] * F, false, log_tab);
+            for (int i = 0; i < 4; ++i) x[i] = lam * neg_log1m(uniform32(hi[i]) * F, false, log_tab);
+// (the parameters are re-read from the record INSIDE the out-of-line function: passing lambda / F / 1 - F as
+            // arguments kept six more registers live across the call site and cost C3 2.6 %; measured on one B200, C3 /
+            // C2 full, ms: no refinement 25.5 / 33.8, arguments 26.2 / 32.6, record pointer 25.3 / 31.6)
+            if (__builtin_expect(max(max(hi[0], hi[1]), max(hi[2], hi[3])) >= kExpTailWord, 0)) {  // one lane-quad in 2^18
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (hi[i] >= kExpTailWord) x[i] = exp_tail_rec<SMEM>(d.base, hi[i], sd.s[i], act, &key0, log_tab);
+            }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -307,6 +304,8 @@ __device__ __forceinline__ void sample_extra4(uint32_t meta, uint32_t tab_off, t
         }
         return;
     }
+    // table lookups: 32 bits from ONE QUAD block for the whole lane-quad (tables of <= 4096 entries), else 64 bits
+    // from two PAIR blocks
     if ((meta & 0x7FFFFFu) <= kQuadTableMaxLen) {
         draw32x4(sd, true, j0, act, kTagQuad, key0, hi);
 #pragma unroll

@@ -493,10 +493,10 @@ void mcdp_or_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_
 #define SPEC_TAG_GAM0 0x47414D30u /* 'GAM0' */
 #define SPEC_TAG_GBST 0x47425354u /* 'GBST' */
 #define SPEC_GAMMA_MAX_ATTEMPTS 65536u
-/* width rule of v2: a 32-bit uniform from a QUAD block for tables of at most 4096 entries and exponentials with
- * max_scale <= 16 lambda; 64 bits from a PAIR block otherwise */
+/* width rules of v2: a 32-bit uniform from a QUAD block for tables of at most 4096 entries (64 bits from a PAIR
+ * block beyond); exponentials draw one 32-bit word w, refined by a second word when w lies in the top 2^-20 */
 #define SPEC_QUAD_TABLE_MAX_LEN 4096
-#define SPEC_QUAD_EXP_MAX_RATIO 16.0
+#define SPEC_EXP_TAIL_WORD 0xFFFFF000u
 
 static double spec_u52(uint64_t x) { return ((double)(x >> 12) + 0.5) * 0x1p-52; }
 static double spec_u32(uint32_t w) { return ((double)w + 0.5) * 0x1p-32; }
@@ -526,10 +526,17 @@ static double spec_sample_extra(const or_dist* d, double base, uint32_t act, uin
             return base * d->p0;
         case MCDP_OR_EXPONENTIAL: {
             /* inverse CDF of the law truncated to [0, max_scale] == law of the reference's rejection loop */
-            const double u = d->p1 <= SPEC_QUAD_EXP_MAX_RATIO * d->p0
-                                 ? spec_u32(spec_quad_word(act, seed, 0u, SPEC_TAG_QUAD, stream_key))
-                                 : spec_u52(spec_pair_bits(act, seed, 0u, stream_key));
-            double x = -d->p0 * log1p(-u * d->exp_F);
+            const uint32_t w = spec_quad_word(act, seed, 0u, SPEC_TAG_QUAD, stream_key);
+            double x;
+            if (w >= SPEC_EXP_TAIL_WORD && d->exp_F >= 0x1p-10) {
+                /* far tail: 1 - u = ((2^32 - w) - (w' + 1/2) 2^-32) 2^-32 with the second word w' (draw j = 1) */
+                const uint32_t w2 = spec_quad_word(act, seed, 1u, SPEC_TAG_QUAD, stream_key);
+                const double one_minus_u = ((double)(uint32_t)(0u - w) - spec_u32(w2)) * 0x1p-32;
+                const double one_minus_F = isinf(d->p1) ? 0.0 : exp(-d->p1 / d->p0);
+                x = -d->p0 * log(fma(d->exp_F, one_minus_u, one_minus_F));
+            } else {
+                x = -d->p0 * log1p(-spec_u32(w) * d->exp_F);
+            }
             if (x > d->p1) x = d->p1;
             return x * base;
         }
