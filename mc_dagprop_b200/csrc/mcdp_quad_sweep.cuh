@@ -93,7 +93,9 @@ __device__ __forceinline__ void atoms_add_u32(uint32_t addr, uint32_t v) {
 #endif
 
 // Unroll factor of the unit loop.  1 ships.  2 lets the two register sets of the one-unit-ahead gather alternate
-// instead of being copied (8 moves per unit) at twice the loop's code size: an experiment for the next round.
+// instead of being copied (8 moves per unit) at twice the loop's code size -- measured in round 2 on one B200 (ms,
+// unroll 1 / 2): C3 full 25.5 / 31.5, C3-MT 29.3 / 37.9, C3 reduced 28.2 / 41.1, C4 reduced 540 / 827: the doubled
+// body falls out of the instruction caches.
 #ifndef MCDP_QUAD_UNIT_UNROLL
 #define MCDP_QUAD_UNIT_UNROLL 1
 #endif
@@ -463,7 +465,7 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
                 apply(d);
             } else {
                 double e[4], d[4];
-                sample_extra4<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, sd, key0, log_tab, e);
+                sample_extra4<SMEM, kReduced>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, sd, key0, log_tab, e);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) d[i] = __dadd_rn(base, e[i]);  // _core.cpp:328
                 apply(d);
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(MCDP_QUAD_MAX_THREADS, 1) quad_sweep_kernel(co
             double d[4] = {base, base, base, base};
             if ((meta >> 29) != kKindNone) {
                 double e[4];
-                sample_extra4<SMEM>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, sd, key0, log_tab, e);
+                sample_extra4<SMEM, kReduced>(meta, uint32_t(q1.y), dists, uint32_t(q1.w), tab, base, act, sd, key0, log_tab, e);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) d[k] = __dadd_rn(base, e[k]);
             }

@@ -72,6 +72,13 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return Philox4{c0, c1, c2, c3};
 }
 
+// The same block out of line, for the cold paths of the samplers (seeds that are not an aligned run of four, redraws
+// after a truncation): ~100 instructions that would otherwise be inlined at every such site and weigh on the
+// register allocation and the instruction footprint of the sweep loop.
+__device__ __noinline__ Philox4 philox4x32_10_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys* key0) {
+    return philox4x32_10(c0, c1, c2, c3, *key0);
+}
+
 // ((X >> 12) + 0.5) * 2^-52 for X = hi:lo, in (0,1): one exact subtraction, no int->fp conversion.
 __device__ __forceinline__ double uniform52(uint32_t lo, uint32_t hi) {
     const uint32_t khi = hi >> 12;

@@ -21,7 +21,19 @@ struct Seeds4 {
     bool quad, quad4;
 };
 
+// Cold paths -- seeds that are not an aligned run of four, redraws after a truncation -- exist in two builds: inlined,
+// or behind out-of-line calls (OOL).  Measured on one B200 (ms, inlined / out of line): C3 full 25.45 / 25.72, C2 full
+// 31.6 / 32.5, C3-MT 29.3 / 29.8, C3 reduced 28.7 / 28.1, C5 reduced 170.0 / 170.5: the calls cost the full-output
+// kernels their register allocation, the smaller code helps the reduced kernels, whose close (statistics) is large.
+// The sweep kernels pick per mode.
+template <bool OOL>
+__device__ __forceinline__ Philox4 philox_cold(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& key0) {
+    if constexpr (OOL) return philox4x32_10_call(c0, c1, c2, c3, &key0);
+    else return philox4x32_10(c0, c1, c2, c3, key0);
+}
+
 // one 32-bit draw per sample from QUAD-style blocks with tag `tag`, draw index j[i]
+template <bool OOL>
 __device__ __forceinline__ void draw32x4(const Seeds4& sd, bool same_j, const uint32_t (&j)[4], uint32_t act, uint32_t tag,
                                          const PhiloxKeys& key0, uint32_t (&w)[4]) {
     if (sd.quad4 && same_j) {
@@ -32,11 +44,12 @@ __device__ __forceinline__ void draw32x4(const Seeds4& sd, bool same_j, const ui
         w[3] = r.w;
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) w[i] = philox_word(philox4x32_10(sd.s[i] >> 2, act, j[i], tag, key0), sd.s[i] & 3u);
+        for (int i = 0; i < 4; ++i) w[i] = philox_word(philox_cold<OOL>(sd.s[i] >> 2, act, j[i], tag, key0), sd.s[i] & 3u);
     }
 }
 
 // one 64-bit draw per sample from PAIR-style blocks with tag `tag`, draw index j[i]
+template <bool OOL>
 __device__ __forceinline__ void draw64x4(const Seeds4& sd, bool same_j, const uint32_t (&j)[4], uint32_t act, uint32_t tag,
                                          const PhiloxKeys& key0, uint32_t (&lo)[4], uint32_t (&hi)[4]) {
     if (sd.quad && same_j) {
@@ -54,7 +67,7 @@ __device__ __forceinline__ void draw64x4(const Seeds4& sd, bool same_j, const ui
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const Philox4 r = philox4x32_10(sd.s[i] >> 1, act, j[i], tag, key0);
+            const Philox4 r = philox_cold<OOL>(sd.s[i] >> 1, act, j[i], tag, key0);
             const bool odd = sd.s[i] & 1u;
             lo[i] = odd ? r.z : r.x;
             hi[i] = odd ? r.w : r.y;
@@ -141,17 +154,17 @@ __device__ __forceinline__ void erlang_value4(const DistView<SMEM>& d, int varia
 }
 
 // draw j[i] of the four samples (erlang_draw2 widened; same blocks and word order)
-template <bool SMEM>
+template <bool SMEM, bool OOL>
 __device__ __forceinline__ void erlang_draw4(const DistView<SMEM>& d, int variant, const Seeds4& sd, bool same_j,
                                              const uint32_t (&j)[4], uint32_t act, const PhiloxKeys& key0, uint32_t log_tab,
                                              double (&y)[4]) {
     uint32_t w0[4], w1[4], w2[4] = {0u, 0u, 0u, 0u}, w3[4] = {0u, 0u, 0u, 0u};
     if (variant == 2) {  // one 32-bit uniform per sample: a QUAD-style block
-        draw32x4(sd, same_j, j, act, kTagErlang, key0, w0);
+        draw32x4<OOL>(sd, same_j, j, act, kTagErlang, key0, w0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) w1[i] = 0u;
     } else if (variant == 1 || variant == 4) {  // 64 bits per sample: PAIR-style blocks
-        draw64x4(sd, same_j, j, act, kTagErlang, key0, w0, w1);
+        draw64x4<OOL>(sd, same_j, j, act, kTagErlang, key0, w0, w1);
     } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -165,15 +178,53 @@ __device__ __forceinline__ void erlang_draw4(const DistView<SMEM>& d, int varian
     erlang_value4<SMEM>(d, variant, w0, w1, w2, w3, log_tab, y);
 }
 
+// Truncation redraws of ONE sample (_core.cpp:98-104: draws 1, 2, ... until x <= max_scale), out of line: rare, and
+// inlined (a second copy of every variant body and of the block generators) it was the largest cold region of the loop.
+// Same blocks and word order as erlang_draw4 / erlang_draw2 use for draw j of this seed.
 template <bool SMEM>
+__device__ __noinline__ double erlang_redraw1(typename Mem<SMEM>::ptr rec, uint32_t seed, uint32_t act, const PhiloxKeys* key0,
+                                              uint32_t log_tab) {
+    const DistView<SMEM> d{rec};
+    const int variant = 2 * d.pad0() + d.pad1();
+    const double mx = d.p(2);
+    double x = 0.0;
+    for (uint32_t j = 1u; j < kGammaMaxAttempts; ++j) {
+        uint32_t w0, w1 = 0u, w2 = 0u, w3 = 0u;
+        if (variant == 2) {
+            w0 = philox_word(philox4x32_10(seed >> 2, act, j, kTagErlang, *key0), seed & 3u);
+        } else if (variant == 1 || variant == 4) {
+            const Philox4 r = philox4x32_10(seed >> 1, act, j, kTagErlang, *key0);
+            const bool odd = seed & 1u;
+            w0 = odd ? r.z : r.x;
+            w1 = odd ? r.w : r.y;
+        } else {
+            const Philox4 r = philox4x32_10(seed, act, j, kTagErlang, *key0);
+            w0 = r.x;
+            w1 = r.y;
+            w2 = r.z;
+            w3 = r.w;
+        }
+        x = erlang_value<SMEM>(d, variant, w0, w1, w2, w3, log_tab);
+        if (!(x > mx)) return x;
+    }
+    return x > mx ? mx : x;  // only after the attempt cap
+}
+
+template <bool SMEM, bool OOL>
 __device__ __forceinline__ void erlang_variate4(const DistView<SMEM>& d, const Seeds4& sd, uint32_t act,
                                                 const PhiloxKeys& key0, uint32_t log_tab, double (&x)[4]) {
     const int variant = 2 * d.pad0() + d.pad1();
     const double mx = d.p(2);
     uint32_t j[4] = {0u, 0u, 0u, 0u};
-    erlang_draw4<SMEM>(d, variant, sd, true, j, act, key0, log_tab, x);
+    erlang_draw4<SMEM, OOL>(d, variant, sd, true, j, act, key0, log_tab, x);
     // truncation (_core.cpp:98-104): draws 1, 2, ... until x <= max_scale; rare, so off the straight path
-    if (__any_sync(0xFFFFFFFFu, any_gt4(x, mx))) {
+    if constexpr (OOL) {
+        if (__builtin_expect(any_gt4(x, mx), 0)) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (x[i] > mx) x[i] = erlang_redraw1<SMEM>(d.base, sd.s[i], act, &key0, log_tab);
+        }
+    } else if (__any_sync(0xFFFFFFFFu, any_gt4(x, mx))) {
         bool need[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) need[i] = x[i] > mx;
@@ -181,7 +232,7 @@ __device__ __forceinline__ void erlang_variate4(const DistView<SMEM>& d, const S
 #pragma unroll
             for (int i = 0; i < 4; ++i) j[i] += need[i] ? 1u : 0u;
             double y[4];
-            erlang_draw4<SMEM>(d, variant, sd, j[0] == j[1] && j[1] == j[2] && j[2] == j[3], j, act, key0, log_tab, y);
+            erlang_draw4<SMEM, OOL>(d, variant, sd, j[0] == j[1] && j[1] == j[2] && j[2] == j[3], j, act, key0, log_tab, y);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (need[i]) {
@@ -198,7 +249,7 @@ __device__ __forceinline__ void erlang_variate4(const DistView<SMEM>& d, const S
 // Marsaglia-Tsang for four samples: the first attempts come out of the two GAM0 blocks of the lane's seed pairs (one
 // Box-Muller pair each: cos branch even seed, sin branch odd seed) and run in lockstep; then ONE warp-wide retry loop
 // in which every lane retries its first pending sample from that sample's SOLO blocks (gamma_variate2 widened).
-template <bool SMEM>
+template <bool SMEM, bool OOL>
 __device__ __forceinline__ void gamma_variate4(const DistView<SMEM>& d, const Seeds4& sd, uint32_t act,
                                                const PhiloxKeys& key0, double (&x)[4]) {
     float nf[4];
@@ -216,11 +267,11 @@ __device__ __forceinline__ void gamma_variate4(const DistView<SMEM>& d, const Se
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) gam0_take(philox4x32_10(sd.s[i] >> 1, act, 0u, kTagGam0, key0), sd.s[i], nf[i], wacc[i]);
+        for (int i = 0; i < 4; ++i) gam0_take(philox_cold<OOL>(sd.s[i] >> 1, act, 0u, kTagGam0, key0), sd.s[i], nf[i], wacc[i]);
     }
     if (d.flags() & 1) {
         const uint32_t j0[4] = {0u, 0u, 0u, 0u};
-        draw32x4(sd, true, j0, act, kTagGbst, key0, wboost);
+        draw32x4<OOL>(sd, true, j0, act, kTagGbst, key0, wboost);
     }
     bool need[4];
     gamma_first_attempts<SMEM, 4>(d, nf, wacc, wboost, x, need);
@@ -249,7 +300,7 @@ __device__ __forceinline__ void gamma_variate4(const DistView<SMEM>& d, const Se
 }
 
 // Extra delays of one activity for the four samples of a lane (sample_extra2 widened).
-template <bool SMEM>
+template <bool SMEM, bool OOL>
 __device__ __forceinline__ void sample_extra4(uint32_t meta, uint32_t tab_off, typename Mem<SMEM>::ptr dists, uint32_t dist,
                                               typename Mem<SMEM>::ptr tab, double base, uint32_t act, const Seeds4& sd,
                                               const PhiloxKeys& key0, uint32_t log_tab, double (&e)[4]) {
@@ -265,9 +316,9 @@ __device__ __forceinline__ void sample_extra4(uint32_t meta, uint32_t tab_off, t
         const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
         double x[4];
         if (d.flags() & 8)
-            erlang_variate4<SMEM>(d, sd, act, key0, log_tab, x);
+            erlang_variate4<SMEM, OOL>(d, sd, act, key0, log_tab, x);
         else
-            gamma_variate4<SMEM>(d, sd, act, key0, x);
+            gamma_variate4<SMEM, OOL>(d, sd, act, key0, x);
 #pragma unroll
         for (int i = 0; i < 4; ++i) e[i] = __dmul_rn(x[i], base);
         return;
@@ -279,7 +330,7 @@ __device__ __forceinline__ void sample_extra4(uint32_t meta, uint32_t tab_off, t
         // inverse CDF of the exponential truncated to [0, max_scale] (see sample_extra2; _core.cpp:83-89): ONE QUAD
         // block for the lane's four samples; a sample in the top 2^-20 is refined out of line (exp_tail)
         const DistView<SMEM> d{dists + dist * uint32_t(sizeof(DistRec))};
-        draw32x4(sd, true, j0, act, kTagQuad, key0, hi);
+        draw32x4<OOL>(sd, true, j0, act, kTagQuad, key0, hi);
         const double lam = d.p(0), mx = d.p(1), F = d.p(2);
         double x[4];
         if (d.flags() & 2) {
@@ -307,12 +358,12 @@ __device__ __forceinline__ void sample_extra4(uint32_t meta, uint32_t tab_off, t
     // table lookups: 32 bits from ONE QUAD block for the whole lane-quad (tables of <= 4096 entries), else 64 bits
     // from two PAIR blocks
     if ((meta & 0x7FFFFFu) <= kQuadTableMaxLen) {
-        draw32x4(sd, true, j0, act, kTagQuad, key0, hi);
+        draw32x4<OOL>(sd, true, j0, act, kTagQuad, key0, hi);
 #pragma unroll
         for (int i = 0; i < 4; ++i) u[i] = uniform32(hi[i]);
     } else {
         uint32_t lo[4];
-        draw64x4(sd, true, j0, act, kTagPair, key0, lo, hi);
+        draw64x4<OOL>(sd, true, j0, act, kTagPair, key0, lo, hi);
 #pragma unroll
         for (int i = 0; i < 4; ++i) u[i] = uniform52(lo[i], hi[i]);
     }
