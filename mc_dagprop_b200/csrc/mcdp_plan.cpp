@@ -137,16 +137,28 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                 r.guide_log2 = g;
                 const size_t gd = guide_doubles(uint32_t(g));
                 r.tab_off = int32_t(out.tab_pool.size());
-                out.tab_pool.resize(out.tab_pool.size() + gd + 2 * size_t(n), 0.0);
+                out.tab_pool.resize(out.tab_pool.size() + gd + 2 * size_t(n) + (size_t(n) + 1) / 2, 0.0);
                 uint32_t* guide = reinterpret_cast<uint32_t*>(out.tab_pool.data() + r.tab_off);
                 double* cp = out.tab_pool.data() + r.tab_off + gd;
                 double* v = cp + n;
+                uint32_t* thr = reinterpret_cast<uint32_t*>(v + n);
                 std::copy(vals, vals + n, v);
+                // Integer form of the boundaries for draws from ONE 32-bit word w (tables of <= kQuadTableMaxLen entries):
+                // with u = (w + 1/2) 2^-32,  cp[i] < u  <=>  w > cp[i] 2^32 - 1/2  <=>  w > thr[i] = floor(cp[i] 2^32 - 1/2)
+                // exactly, so the device compares integers and never forms u.  Boundaries below 2^-33 (thr would be -1)
+                // can never be the lower bound of a representable u: thr 0 and the guide skips them.
+                auto fill_thresholds = [&] {
+                    for (int64_t i = 0; i < n; ++i) {
+                        const long double x = static_cast<long double>(cp[i]) * 4294967296.0L - 0.5L;
+                        thr[i] = x < 0.0L ? 0u : uint32_t(std::min<long double>(std::floor(x), 4294967295.0L));
+                    }
+                };
                 if (n < 2) {
                     // std::discrete_distribution with < 2 weights always returns index 0
                     // (libstdc++ random.tcc:2660-2664,2703-2704).
                     cp[0] = 1.0;
                     guide[0] = guide[1] = 0;
+                    fill_thresholds();
                     break;
                 }
                 // libstdc++ random.tcc:2655-2678: normalise, partial sums, last = 1 -- same
@@ -170,14 +182,18 @@ bool build_dists(const mcdp_dists_desc& d, HostPlan& out, std::unordered_map<int
                     cp[i] = acc;
                 }
                 cp[n - 1] = 1.0;
-                // guide[j] = first i with cp[i] >= j / G
+                // guide[j] = first i with cp[i] >= j / G (tables drawn from 32-bit words: and >= 2^-33, the smallest u such a
+                // draw can form)
                 const int64_t G = int64_t(1) << g;
                 int64_t i = 0;
+                if (n <= int64_t(kQuadTableMaxLen))
+                    while (i + 1 < n && cp[i] < 0x1p-33) ++i;
                 for (int64_t j = 0; j < G; ++j) {
                     const double edge = double(j) / double(G);
                     while (cp[i] < edge) ++i;
                     guide[j] = uint32_t(i);
                 }
+                fill_thresholds();
                 break;
             }
             default:

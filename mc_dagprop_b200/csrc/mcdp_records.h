@@ -33,7 +33,8 @@ static_assert(sizeof(EventRec) == 32, "EventRec must be 32 bytes");
 // table lookup do not wait on a dependent DistRec load.
 //   meta = kind << 29 | guide_log2 << 24 | scan << 23 | table_len      (kind 5 = no distribution;
 //          scan = 1 when a guide bucket may hold more than one cumulative boundary)
-//   table block in the pool: [guide: 2^g u32][cp: len f64][values: len f64]; for table kinds
+//   table block in the pool: [guide: 2^g u32][cp: len f64][values: len f64][thr: len u32 (integer boundaries for
+//   32-bit draws, padded to 8 bytes)]; for table kinds
 //   `tab_off` is the BYTE offset of the guide and `dist` the BYTE offset of cp (values follow cp)
 struct alignas(16) PredRec {
     uint32_t src_row;   // row of the source event's realized time; in full/injected mode also the value of cause_event

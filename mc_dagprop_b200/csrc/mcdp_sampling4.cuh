@@ -75,6 +75,28 @@ __device__ __forceinline__ void draw64x4(const Seeds4& sd, bool same_j, const ui
     }
 }
 
+// The same lookup for draws from one 32-bit word: the boundaries are compared as integers (thr[i] = floor(cp[i] 2^32
+// - 1/2): w > thr[i] <=> cp[i] < (w + 1/2) 2^-32, exactly), the uniform is never formed.
+template <bool SMEM>
+__device__ __forceinline__ void emp_value4_narrow(typename Mem<SMEM>::ptr guide_b, typename Mem<SMEM>::ptr cp_b, uint32_t g,
+                                                  uint32_t len8, bool scan, const uint32_t (&w)[4], double (&v)[4]) {
+    const typename Mem<SMEM>::ptr thr_b = cp_b + 2u * len8;
+    uint32_t idx[4], t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) idx[i] = Mem<SMEM>::u32(guide_b + (w[i] >> (32u - g)) * 4u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t[i] = Mem<SMEM>::u32(thr_b + idx[i] * 4u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) idx[i] += w[i] > t[i] ? 1u : 0u;  // thr[len-1] == 2^32 - 1: stays in range
+    if (scan) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            while (w[i] > Mem<SMEM>::u32(thr_b + idx[i] * 4u)) ++idx[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = Mem<SMEM>::f64(cp_b + idx[i] * 8u + len8);
+}
+
 // inverse-CDF lookup of four samples in lockstep (emp_value2 widened)
 template <bool SMEM>
 __device__ __forceinline__ void emp_value4(typename Mem<SMEM>::ptr guide_b, typename Mem<SMEM>::ptr cp_b, uint32_t g,
@@ -357,23 +379,22 @@ __device__ __forceinline__ void sample_extra4(uint32_t meta, uint32_t tab_off, t
     }
     // table lookups: 32 bits from ONE QUAD block for the whole lane-quad (tables of <= 4096 entries), else 64 bits
     // from two PAIR blocks
-    if ((meta & 0x7FFFFFu) <= kQuadTableMaxLen) {
-        draw32x4<OOL>(sd, true, j0, act, kTagQuad, key0, hi);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) u[i] = uniform32(hi[i]);
-    } else {
-        uint32_t lo[4];
-        draw64x4<OOL>(sd, true, j0, act, kTagPair, key0, lo, hi);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) u[i] = uniform52(lo[i], hi[i]);
-    }
     // empirical tables (pool block layout: see sample_extra2)
     const uint32_t g = (meta >> 24) & 31u, len8 = (meta & 0x7FFFFFu) * 8u;
     const bool scan = meta & 0x800000u;
     const typename Mem<SMEM>::ptr guide_b = tab + tab_off;
     const typename Mem<SMEM>::ptr cp_b = tab + dist;
     double v[4];
-    emp_value4<SMEM>(guide_b, cp_b, g, len8, scan, hi, u, v);
+    if ((meta & 0x7FFFFFu) <= kQuadTableMaxLen) {
+        draw32x4<OOL>(sd, true, j0, act, kTagQuad, key0, hi);
+        emp_value4_narrow<SMEM>(guide_b, cp_b, g, len8, scan, hi, v);
+    } else {
+        uint32_t lo[4];
+        draw64x4<OOL>(sd, true, j0, act, kTagPair, key0, lo, hi);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) u[i] = uniform52(lo[i], hi[i]);
+        emp_value4<SMEM>(guide_b, cp_b, g, len8, scan, hi, u, v);
+    }
     if (kind == MCDP_DIST_EMP_ABS) {  // _core.cpp:125
 #pragma unroll
         for (int i = 0; i < 4; ++i) e[i] = v[i];
