@@ -1,10 +1,9 @@
-"""Containers of the analytic propagator and their validation (reference ``analytic/_context.py``)."""
+"""Containers of the analytic propagator (reference ``analytic/_context.py:14-90``); the validation of a context is
+in ``_validate.py``."""
 from __future__ import annotations
 
 from dataclasses import dataclass
 from enum import IntEnum, unique
-
-import numpy as np
 
 from ..monte_carlo import Event
 from ..types import ActivityIndex, EventIndex, ProbabilityMass, Second
@@ -62,52 +61,4 @@ class AnalyticContext:
     max_delay: Second | None = None
 
 
-def validate_context(context: AnalyticContext) -> None:
-    """Structural checks of the reference (``_context.py:93-158``): step, ``max_delay``, event windows, activity
-    indices / alignment / unit mass, precedence indices and acyclicity.  Every violation is a ``ValueError``."""
-    n = len(context.events)
-    if context.step <= 0.0:
-        raise ValueError("step_size must be positive")
-    if context.max_delay is not None and context.max_delay < 0.0:
-        raise ValueError("max_delay must be non-negative when provided")
-    for i, ev in enumerate(context.events):
-        ts = ev.timestamp
-        if ts.earliest > ts.latest:
-            raise ValueError(f"event {i} has earliest > latest")
-        if not (ts.earliest <= ts.actual <= ts.latest):
-            raise ValueError(f"event {i} actual time outside bounds")
-    for (src, dst), (_, edge) in context.activities.items():
-        if not (0 <= src < n and 0 <= dst < n):
-            raise ValueError(f"activity {(src, dst)} references invalid node")
-        edge.pmf.validate()
-        if not np.isclose(edge.pmf.step, context.step):
-            raise ValueError(f"edge {(src, dst)} step {edge.pmf.step} does not match context step size {context.step}")
-        edge.pmf.validate_alignment(context.step)
-        if not np.isclose(edge.pmf.total_mass, 1.0):
-            raise ValueError(f"activity {(src, dst)} PMF does not sum to 1, got {edge.pmf.total_mass}")
-    indegree = [0] * n
-    successors: list[list[int]] = [[] for _ in range(n)]
-    for target, preds in context.precedence_list:
-        if not (0 <= target < n):
-            raise ValueError(f"target index {target} out of range")
-        for src, link in preds:
-            if not (0 <= src < n):
-                raise ValueError(f"predecessor index {src} out of range")
-            edge = context.activities.get((src, target))
-            if edge is None:
-                raise ValueError(f"missing activity for {(src, target)}")
-            if edge[0] != link:
-                raise ValueError(f"edge index {link} for {(src, target)} does not match context mapping {edge[0]}")
-            successors[src].append(target)
-            indegree[target] += 1
-    ready = [i for i, deg in enumerate(indegree) if deg == 0]
-    seen = 0
-    while ready:
-        node = ready.pop()
-        seen += 1
-        for dst in successors[node]:
-            indegree[dst] -= 1
-            if indegree[dst] == 0:
-                ready.append(dst)
-    if seen != n:
-        raise ValueError("precedence list contains a cycle")
+from ._validate import validate_context  # noqa: E402,F401  (the checks live in their own module)
