@@ -41,12 +41,14 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     deps = _sources(".cu", ".cuh", ".cpp", ".hpp", ".h", ".inl")
     deps = [d for d in deps if not d.endswith("pybind_core.cpp")]
     if force or _newer(LIB, deps):
+        tmp = LIB + ".tmp"  # compiled beside the target and renamed: a process that has the old file mapped keeps it
         cmd = [NVCC, "-O3", "-std=c++17", *ARCH_FLAGS, "-lineinfo", "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-O3,-Wall",
-               "-shared", "-cudart", "static", "-o", LIB, *os.environ.get("MCDP_NVCC_EXTRA", "").split(),
+               "-shared", "-cudart", "static", "-o", tmp, *os.environ.get("MCDP_NVCC_EXTRA", "").split(),
                os.path.join(CSRC, "mcdp_capi.cu"), os.path.join(CSRC, "mcdp_analytic.cu"), os.path.join(CSRC, "mcdp_plan.cpp")]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)
+        os.replace(tmp, LIB)
     return LIB
 
 
@@ -64,8 +66,9 @@ def build_core(force: bool = False) -> str:
     if force or _newer(out, [src, os.path.join(ROOT, "include", "mcdp_b200.h"), LIB]):
         cmd = [HOST_CXX, "-O2", "-std=c++20", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall",
                f"-I{pybind11.get_include()}", f"-I{sysconfig.get_paths()['include']}", f"-I{os.path.join(ROOT, 'include')}",
-               "-o", out, src, f"-L{PKG}", "-lmcdp_b200", "-Wl,-rpath,$ORIGIN/.."]
+               "-o", out + ".tmp", src, f"-L{PKG}", "-lmcdp_b200", "-Wl,-rpath,$ORIGIN/.."]
         subprocess.run(cmd, check=True)
+        os.replace(out + ".tmp", out)
     return out
 
 
