@@ -264,6 +264,12 @@ int64_t mcdp_analytic_out_capacity(const mcdp_analytic_desc* desc, int64_t* out_
  * checks (cycle, no bound bin to truncate onto, empty PMF) return MCDP_ERR_INVALID with its message. */
 int32_t mcdp_analytic_run(const mcdp_analytic_desc* desc, int32_t device, int64_t* out_start, int32_t* out_len, int64_t* out_off,
                           double* out_probs, int64_t out_cap, double* underflow, double* overflow);
+
+/* Phases of this thread's last mcdp_analytic_run, in milliseconds: out5[0] host preparation (precedence by event,
+ * levels, output slots), [1] device allocations and uploads, [2] the level kernels (all launches, synchronised),
+ * [3] results to the host; out5[4] = number of levels (= kernel launches).  Measurement aid of scripts/bench_analytic.py;
+ * the reference has no counterpart. */
+int32_t mcdp_analytic_last_profile(double* out5);
 /* A single PMF operation on the device: op 0 = convolve(a, b), 1 = maximum(a, b), 2 = clip a to [min_value, max_value]
  * with the flow rules (b unused). */
 int32_t mcdp_pmf_op(int32_t op, int32_t device, int64_t step, int64_t a_start, int32_t a_len, const double* a_probs, int64_t b_start,

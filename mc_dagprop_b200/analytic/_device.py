@@ -45,6 +45,7 @@ def _lib():
         L.mcdp_analytic_out_capacity.argtypes = [C.POINTER(AnalyticDesc), vp]
         L.mcdp_analytic_out_capacity.restype = i64
         L.mcdp_analytic_run.argtypes = [C.POINTER(AnalyticDesc), i32, vp, vp, vp, vp, i64, vp, vp]
+        L.mcdp_analytic_last_profile.argtypes = [C.POINTER(C.c_double)]
         L.mcdp_pmf_op.argtypes = [i32, i32, i64, i64, i32, vp, i64, i32, vp, i64, i64, i32, i32, vp, vp, vp, i64, vp, vp]
         _bound = True
     return L
@@ -56,6 +57,14 @@ def _raise(rc: int) -> None:
     if rc == capi.MCDP_ERR_INVALID and "cycle" not in msg:
         raise ValueError(msg)
     raise RuntimeError(msg)
+
+
+def last_profile() -> dict:
+    """Phases of this thread's last ``analytic_run`` in milliseconds (``mcdp_analytic_last_profile``)."""
+    out = (C.c_double * 5)()
+    _lib().mcdp_analytic_last_profile(out)
+    return {"host_prepare_ms": out[0], "alloc_upload_ms": out[1], "level_kernels_ms": out[2], "download_ms": out[3],
+            "levels": int(out[4])}
 
 
 def pmf_op(op: int, step: int, a_start: int, a_probs: np.ndarray, b_start: int = 0, b_probs: np.ndarray | None = None,

@@ -56,6 +56,15 @@ class DiscretePMF:
 
     # -- construction helpers ------------------------------------------------------------------------
     @staticmethod
+    def _unchecked(values: np.ndarray, probabilities: np.ndarray, step: int) -> "DiscretePMF":
+        """For results of the device engine whose checks were done in bulk (``AnalyticPropagator.run``)."""
+        pmf = object.__new__(DiscretePMF)
+        object.__setattr__(pmf, "values", values)
+        object.__setattr__(pmf, "probabilities", probabilities)
+        object.__setattr__(pmf, "step", step)
+        return pmf
+
+    @staticmethod
     def delta(v: Second, step: Second) -> "DiscretePMF":
         """A unit mass at ``v``."""
         return DiscretePMF(np.array([v], dtype=float), np.array([1.0], dtype=float), step=step)

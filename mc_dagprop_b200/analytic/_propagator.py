@@ -58,6 +58,7 @@ class AnalyticPropagator:
     context: AnalyticContext
     _predecessors_by_target: tuple[tuple[PredecessorTuple, ...] | None, ...]
     _topological_node_order: tuple[EventIndex, ...]
+    _flat: tuple | None = None  # the context as device-call arrays (filled by the first run)
 
     @property
     def underflow_rule(self) -> UnderflowRule:
@@ -68,21 +69,26 @@ class AnalyticPropagator:
         return self.context.overflow_rule
 
     def _event_bounds(self, earliest: Second, latest: Second) -> tuple[int, int]:
+        """Integer bounds of one event (reference ``_propagator.py:150-156``); ``_flatten`` does all events at once."""
         upper = latest
         if self.context.max_delay is not None:
             upper = min(latest, earliest + self.context.max_delay)
         return int(np.round(earliest)), int(np.round(upper))
 
-    def run(self) -> tuple[SimulatedEvent, ...]:
-        """One ``SimulatedEvent`` per event, in the order of ``context.events``."""
+    def _flatten(self) -> tuple:
+        """The context as the arrays ``mcdp_analytic_run`` takes: integer bounds and origins of every event, the
+        precedence list in CSR form, one PMF per distinct activity object in first-use order.  Contexts are immutable,
+        so this is done once per propagator."""
+        if self._flat is not None:
+            return self._flat
         ctx = self.context
         step = ctx.step
-        n = len(ctx.events)
-        lower, upper, origin = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.int64)
-        for i, ev in enumerate(ctx.events):
-            lower[i], upper[i] = self._event_bounds(ev.timestamp.earliest, ev.timestamp.latest)
-            origin[i] = int(round(round(ev.timestamp.earliest / step) * step))
-        # one PMF per distinct activity object, in first-use order
+        earliest = np.array([ev.timestamp.earliest for ev in ctx.events], dtype=float)
+        latest = np.array([ev.timestamp.latest for ev in ctx.events], dtype=float)
+        if ctx.max_delay is not None:
+            latest = np.minimum(latest, earliest + ctx.max_delay)
+        lower, upper = np.round(earliest).astype(np.int64), np.round(latest).astype(np.int64)
+        origin = np.round(np.round(earliest / step) * step).astype(np.int64)
         pmf_index: dict[int, int] = {}
         pmf_start: list[int] = []
         pmf_probs: list[np.ndarray] = []
@@ -92,25 +98,42 @@ class AnalyticPropagator:
                 continue
             targets.append(target)
             for src, _ in preds:
-                activity = ctx.activities[(src, target)][1]
-                key = id(activity.pmf)
-                if key not in pmf_index:
-                    pmf_index[key] = len(pmf_start)
-                    pmf_start.append(int(round(float(activity.pmf.values[0]))))
-                    pmf_probs.append(np.ascontiguousarray(activity.pmf.probabilities, np.float64))
+                pmf = ctx.activities[(src, target)][1].pmf
+                slot = pmf_index.get(id(pmf))
+                if slot is None:
+                    slot = pmf_index[id(pmf)] = len(pmf_start)
+                    pmf_start.append(int(round(float(pmf.values[0]))))
+                    pmf_probs.append(np.ascontiguousarray(pmf.probabilities, np.float64))
                 srcs.append(src)
-                pmfs.append(pmf_index[key])
+                pmfs.append(slot)
             offsets.append(len(srcs))
-        pmf_off = np.concatenate([[0], np.cumsum([p.size for p in pmf_probs])]).astype(np.int64)
-        flat = np.concatenate(pmf_probs) if pmf_probs else np.zeros(0)
+        pmf_off = np.zeros(len(pmf_probs) + 1, np.int64)
+        np.cumsum([p.size for p in pmf_probs], out=pmf_off[1:])
+        flat = (lower, upper, origin, int(step), np.asarray(targets, np.int32), np.asarray(offsets, np.int64),
+                np.asarray(srcs, np.int32), np.asarray(pmfs, np.int32), np.asarray(pmf_start, np.int64), pmf_off,
+                np.concatenate(pmf_probs) if pmf_probs else np.zeros(0))
+        object.__setattr__(self, "_flat", flat)
+        return flat
+
+    def run(self) -> tuple[SimulatedEvent, ...]:
+        """One ``SimulatedEvent`` per event, in the order of ``context.events``."""
+        step = self.context.step
         start, length, off, probs, under, over = _device.analytic_run(
-            lower, upper, origin, int(step), targets, offsets, srcs, pmfs, pmf_start, pmf_off, flat,
-            int(self.underflow_rule), int(self.overflow_rule))
+            *self._flatten(), int(self.underflow_rule), int(self.overflow_rule))
+        # the checks of the reference's DiscretePMF constructor (_pmf.py:38-52) for all events at once: the grids are
+        # ascending by construction, every event has at least one bin, what is left to check is the mass
+        n = len(length)
+        if n:
+            mass = np.add.reduceat(probs, off[:-1]) if probs.size else np.zeros(n)
+            if np.any((mass > 1.0) & ~np.isclose(mass, 1.0)):
+                raise ValueError("Probabilities must sum to <= 1.0")
+        grid = np.arange(int(length.max()) if n else 0, dtype=float) * float(step)
         out = []
         for i in range(n):
-            p = probs[off[i]: off[i] + length[i]].copy()
-            values = float(start[i]) + float(step) * np.arange(p.size, dtype=float)
-            out.append(SimulatedEvent(DiscretePMF(values, p, step=step), ProbabilityMass(under[i]), ProbabilityMass(over[i])))
+            k = int(length[i])
+            o = int(off[i])
+            pmf = DiscretePMF._unchecked(float(start[i]) + grid[:k], probs[o:o + k], step)
+            out.append(SimulatedEvent(pmf, ProbabilityMass(under[i]), ProbabilityMass(over[i])))
         return tuple(out)
 
     def _convert_to_simulated_event(self, pmf: DiscretePMF, min_value: int, max_value: int) -> SimulatedEvent:

@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = (
     "mcdp_plan_get_chunks", "mcdp_plan_launch_shape", "mcdp_plan_reduced_chunk", "mcdp_run_attribution_device", "mcdp_run_attribution_host", "mcdp_host_alloc", "mcdp_host_free",
     "mcdp_planset_create", "mcdp_planset_destroy", "mcdp_planset_size", "mcdp_planset_plan", "mcdp_planset_set_option",
     "mcdp_run_many_host_multi", "mcdp_run_injected_host_multi", "mcdp_run_reduced_host_multi", "mcdp_run_attribution_host_multi",
-    "mcdp_analytic_out_capacity", "mcdp_analytic_run", "mcdp_pmf_op",
+    "mcdp_analytic_out_capacity", "mcdp_analytic_run", "mcdp_analytic_last_profile", "mcdp_pmf_op",
 )
 
 

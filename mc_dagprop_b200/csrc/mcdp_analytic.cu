@@ -23,6 +23,7 @@
 #include <nvtx3/nvToolsExt.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <string>
@@ -487,6 +488,19 @@ int64_t mcdp_analytic_out_capacity(const mcdp_analytic_desc* d, int64_t* out_off
     return off;
 }
 
+namespace {
+thread_local double g_profile[5] = {0, 0, 0, 0, 0};  // last mcdp_analytic_run of this thread, see mcdp_analytic_last_profile
+double ms_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+}  // namespace
+
+int32_t mcdp_analytic_last_profile(double* out5) {
+    if (!out5) return mcdp_set_error(MCDP_ERR_ARG, "null argument");
+    std::copy(g_profile, g_profile + 5, out5);
+    return MCDP_OK;
+}
+
 int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* out_start, int32_t* out_len, int64_t* out_off,
                           double* out_probs, int64_t out_cap, double* underflow, double* overflow) {
     if (!d || !out_start || !out_len || !out_off || !out_probs || !underflow || !overflow)
@@ -498,6 +512,8 @@ int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* 
     struct Pop {
         ~Pop() { nvtxRangePop(); }
     } pop;
+    auto t_phase = std::chrono::steady_clock::now();
+    std::fill(g_profile, g_profile + 5, 0.0);
     // precedence by event id (the last entry for a target wins, like the Monte-Carlo compile), bounds-checked
     std::vector<int32_t> entry_of(size_t(E), -1);
     for (int32_t i = 0; i < d->n_prec_entries; ++i) {
@@ -571,6 +587,8 @@ int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* 
     int prev = -1;
     int32_t rc = use_device(device, &prev);
     if (rc) return rc;
+    g_profile[0] = ms_since(t_phase);  // host: precedence by event, levels, output slots
+    t_phase = std::chrono::steady_clock::now();
     {
         DevMem mem;
         AnalyticParams p{};
@@ -622,6 +640,9 @@ int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* 
         p.step = d->step;
         p.under_rule = d->underflow_rule;
         p.over_rule = d->overflow_rule;
+        ACUDA(cudaDeviceSynchronize());
+        g_profile[1] = ms_since(t_phase);  // device allocations and uploads
+        t_phase = std::chrono::steady_clock::now();
         for (size_t l = 0; l + 1 < level_begin.size(); ++l) {
             const int n = level_begin[l + 1] - level_begin[l];
             if (n <= 0) continue;
@@ -629,6 +650,9 @@ int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* 
             ACUDA(cudaGetLastError());
         }
         ACUDA(cudaDeviceSynchronize());
+        g_profile[2] = ms_since(t_phase);  // one launch per level, all levels
+        g_profile[4] = double(level_begin.size() - 1);
+        t_phase = std::chrono::steady_clock::now();
         ACUDA(cudaMemcpy(status.data(), d_status, size_t(E) * 4, cudaMemcpyDeviceToHost));
         for (int32_t e : order) {  // the first failing event in evaluation order, like the reference's loop
             if (status[e] != kClipOk) {
@@ -642,6 +666,7 @@ int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* 
         ACUDA(cudaMemcpy(underflow, d_under, size_t(E) * 8, cudaMemcpyDeviceToHost));
         ACUDA(cudaMemcpy(overflow, d_over, size_t(E) * 8, cudaMemcpyDeviceToHost));
         std::copy(off.begin(), off.end(), out_off);
+        g_profile[3] = ms_since(t_phase);  // results to the host
     }
 done:
     if (prev >= 0 && prev != device) cudaSetDevice(prev);
