@@ -138,9 +138,18 @@ __device__ void block_convolve(const Pmf& a, const Pmf& b, long long step, doubl
         n = a.len + b.len - 1;
         for (int k = threadIdx.x; k < n; k += kThreads) {
             const int j0 = max(0, k - (b.len - 1)), j1 = min(k, a.len - 1);
-            dd acc{0.0, 0.0};
-            for (int j = j0; j <= j1; ++j) acc = dd_add_prod(acc, a.p[j], b.p[k - j]);
-            out[k] = dd_round(acc);
+            // four interleaved double-double accumulators: one dd_add_prod is a chain of nine dependent fp64
+            // operations, a single accumulator would leave the fp64 pipe idle most of the time
+            dd acc0{0.0, 0.0}, acc1{0.0, 0.0}, acc2{0.0, 0.0}, acc3{0.0, 0.0};
+            int j = j0;
+            for (; j + 3 <= j1; j += 4) {
+                acc0 = dd_add_prod(acc0, a.p[j], b.p[k - j]);
+                acc1 = dd_add_prod(acc1, a.p[j + 1], b.p[k - j - 1]);
+                acc2 = dd_add_prod(acc2, a.p[j + 2], b.p[k - j - 2]);
+                acc3 = dd_add_prod(acc3, a.p[j + 3], b.p[k - j - 3]);
+            }
+            for (; j <= j1; ++j) acc0 = dd_add_prod(acc0, a.p[j], b.p[k - j]);
+            out[k] = dd_round(dd_add(dd_add(acc0, acc1), dd_add(acc2, acc3)));
         }
     }
     *o_start = a.start + b.start;
@@ -161,19 +170,26 @@ __device__ void block_cumsum(int n, F x, double* c_hi, double* c_lo, dd* s_seg) 
         c_hi[i] = acc.hi;
         c_lo[i] = acc.lo;
     }
-    __syncthreads();
-    s_seg[threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {  // exclusive scan of the 256 segment totals
-        dd run{0.0, 0.0};
-        for (int t = 0; t < kThreads; ++t) {
-            const dd v = s_seg[t];
-            s_seg[t] = run;
-            run = dd_add(run, v);
-        }
+    // exclusive scan of the 256 segment totals: shuffles inside a warp, then the eight warp totals
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    dd inc = acc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        dd w;
+        w.hi = __shfl_up_sync(0xFFFFFFFFu, inc.hi, o);
+        w.lo = __shfl_up_sync(0xFFFFFFFFu, inc.lo, o);
+        if (lane >= o) inc = dd_add(w, inc);
     }
+    dd exc;
+    exc.hi = __shfl_up_sync(0xFFFFFFFFu, inc.hi, 1);
+    exc.lo = __shfl_up_sync(0xFFFFFFFFu, inc.lo, 1);
+    if (lane == 0) exc = dd{0.0, 0.0};
+    __syncthreads();  // s_seg may still be read by the previous call
+    if (lane == 31) s_seg[warp] = inc;
     __syncthreads();
-    const dd off = s_seg[threadIdx.x];
+    dd before{0.0, 0.0};
+    for (int w = 0; w < warp; ++w) before = dd_add(before, s_seg[w]);
+    const dd off = dd_add(before, exc);
     if (threadIdx.x > 0) {
         for (int i = i0; i < i1; ++i) {
             const dd v = dd_add(off, dd{c_hi[i], c_lo[i]});
@@ -317,7 +333,7 @@ struct AnalyticParams {
     double* underflow;
     double* overflow;
     int32_t* status;           // [E]
-    double* scratch;           // per CTA: 7 arrays of scratch_len
+    double* scratch;           // per CTA: 7 arrays of scratch_len (null: they fit the CTA's dynamic shared memory)
     long long scratch_len;
     long long step;
     int under_rule, over_rule;
@@ -342,7 +358,10 @@ __global__ void __launch_bounds__(kThreads) analytic_level_kernel(const Analytic
         }
         return;
     }
-    double* const base = p.scratch + size_t(blockIdx.x) * 7 * size_t(p.scratch_len);
+    // intermediates of the event: in shared memory when they fit (every step of the chain below is a round trip
+    // through them between two barriers), else in a global scratch slab
+    extern __shared__ double s_scratch[];
+    double* const base = p.scratch ? p.scratch + size_t(blockIdx.x) * 7 * size_t(p.scratch_len) : s_scratch;
     double* conv = base;
     double* run = base + p.scratch_len;
     double* tmp = base + 2 * p.scratch_len;
@@ -616,7 +635,15 @@ int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* 
         ACUDA(mem.alloc(&d_out_probs, size_t(cap)));
         ACUDA(mem.alloc(&d_under, size_t(E)));
         ACUDA(mem.alloc(&d_over, size_t(E)));
-        ACUDA(mem.alloc(&d_scratch, size_t(max_width) * 7 * size_t(scratch_len)));
+        const size_t smem_need = size_t(7) * size_t(scratch_len) * sizeof(double);
+        int smem_max = 0;
+        ACUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        const bool in_smem = smem_need + 8192 <= size_t(smem_max);  // static shared memory of the kernel is below 8 KB
+        if (in_smem) {
+            ACUDA(cudaFuncSetAttribute(analytic_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_need)));
+        } else {
+            ACUDA(mem.alloc(&d_scratch, size_t(max_width) * 7 * size_t(scratch_len)));
+        }
         ACUDA(cudaMemset(d_out_probs, 0, size_t(std::max<int64_t>(cap, 1)) * 8));
         p.order = d_order;
         p.pred_off = d_pred_off;
@@ -646,7 +673,7 @@ int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* 
         for (size_t l = 0; l + 1 < level_begin.size(); ++l) {
             const int n = level_begin[l + 1] - level_begin[l];
             if (n <= 0) continue;
-            analytic_level_kernel<<<unsigned(n), kThreads>>>(p, level_begin[l]);
+            analytic_level_kernel<<<unsigned(n), kThreads, in_smem ? smem_need : 0>>>(p, level_begin[l]);
             ACUDA(cudaGetLastError());
         }
         ACUDA(cudaDeviceSynchronize());

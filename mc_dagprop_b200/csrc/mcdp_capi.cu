@@ -12,6 +12,7 @@
 #include <new>
 #include <string>
 #include <thread>
+#include <system_error>
 #include <unordered_map>
 #include <vector>
 

@@ -80,7 +80,16 @@ int32_t for_each_shard(mcdp_planset* set, int64_t n, F&& call) {
         if (rcs[size_t(i)]) msgs[size_t(i)] = g_err;  // the message is thread-local: hand it to the caller's thread
     };
     std::vector<std::thread> threads;
-    for (int i = 1; i < g; ++i) threads.emplace_back(work, i);
+    for (int i = 1; i < g; ++i) {
+        int64_t lo, hi;
+        shard_block(n, i, g, &lo, &hi);
+        if (hi <= lo) continue;  // a call smaller than the set (run(seed)): no thread for an empty block
+        try {
+            threads.emplace_back(work, i);
+        } catch (const std::system_error&) {
+            work(i);  // no thread to be had: this block runs on the caller's thread
+        }
+    }
     work(0);
     for (auto& t : threads) t.join();
     for (int i = 0; i < g; ++i)
