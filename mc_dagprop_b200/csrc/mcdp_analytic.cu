@@ -37,6 +37,21 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// thread-block cluster: rank of this CTA, CTAs per cluster, barrier with release / acquire ordering of global writes
+__device__ __forceinline__ unsigned cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_size() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- double-double helpers (error-free transformations; explicit intrinsics so that nothing is contracted) ----
 struct dd {
     double hi, lo;
@@ -61,13 +76,6 @@ __device__ __forceinline__ dd dd_add_d(dd x, double y) {
     s.lo = __dadd_rn(s.lo, x.lo);
     return quick_two_sum(s.hi, s.lo);
 }
-__device__ __forceinline__ dd dd_add_prod(dd acc, double a, double b) {  // acc + a * b, the product exact
-    const double p = __dmul_rn(a, b);
-    const double e = __fma_rn(a, b, -p);
-    dd s = two_sum(acc.hi, p);
-    s.lo = __dadd_rn(s.lo, __dadd_rn(acc.lo, e));
-    return quick_two_sum(s.hi, s.lo);
-}
 __device__ __forceinline__ dd dd_mul_d(dd x, double y) {  // (x.hi + x.lo) * y
     const double p = __dmul_rn(x.hi, y);
     const double e = __fma_rn(x.hi, y, -p);
@@ -85,11 +93,10 @@ __device__ __forceinline__ dd warp_sum_dd(dd v) {
     }
     return v;
 }
-// sum of f(i), i in [0, n), over the block; every thread gets the rounded total
-template <typename F>
-__device__ double block_sum(int n, F f, dd* s_part) {
+// sum of p[0..n) over the block in double-double; every thread gets the rounded total
+__device__ double block_sum(const double* p, int n, dd* s_part) {
     dd acc{0.0, 0.0};
-    for (int i = threadIdx.x; i < n; i += kThreads) acc = dd_add_d(acc, f(i));
+    for (int i = threadIdx.x; i < n; i += kThreads) acc = dd_add_d(acc, p[i]);
     acc = warp_sum_dd(acc);
     __syncthreads();
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
@@ -99,6 +106,36 @@ __device__ double block_sum(int n, F f, dd* s_part) {
     for (int w = 0; w < kThreads / 32; ++w) tot = dd_add(tot, s_part[w]);
     return dd_round(tot);
 }
+// two sums in one pass (the same additions in the same order as two block_sum calls, one set of barriers)
+__device__ void block_sum2(const double* p0, int n0, const double* p1, int n1, dd* s_part, double* r0, double* r1) {
+    dd a0{0.0, 0.0}, a1{0.0, 0.0};
+    for (int i = threadIdx.x; i < n0; i += kThreads) a0 = dd_add_d(a0, p0[i]);
+    for (int i = threadIdx.x; i < n1; i += kThreads) a1 = dd_add_d(a1, p1[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        dd w0, w1;
+        w0.hi = __shfl_xor_sync(0xFFFFFFFFu, a0.hi, o);
+        w0.lo = __shfl_xor_sync(0xFFFFFFFFu, a0.lo, o);
+        w1.hi = __shfl_xor_sync(0xFFFFFFFFu, a1.hi, o);
+        w1.lo = __shfl_xor_sync(0xFFFFFFFFu, a1.lo, o);
+        a0 = dd_add(a0, w0);
+        a1 = dd_add(a1, w1);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        s_part[threadIdx.x >> 5] = a0;
+        s_part[kThreads / 32 + (threadIdx.x >> 5)] = a1;
+    }
+    __syncthreads();
+    dd t0{0.0, 0.0}, t1{0.0, 0.0};
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) {
+        t0 = dd_add(t0, s_part[w]);
+        t1 = dd_add(t1, s_part[kThreads / 32 + w]);
+    }
+    *r0 = dd_round(t0);
+    *r1 = dd_round(t1);
+}
 // numpy.isclose(a, b, rtol, atol) for finite values
 __device__ __forceinline__ bool is_close(double a, double b, double rtol, double atol) { return fabs(a - b) <= atol + rtol * fabs(b); }
 
@@ -106,25 +143,67 @@ struct Pmf {
     long long start;  // value of bin 0, seconds
     int len;
     const double* p;
+    double mass;      // block_sum(p, len), or negative: not computed yet
 };
+// masses are computed once where a PMF is produced and travel with it (the reference recomputes total_mass in every
+// operation, _pmf.py:96-105: the same number)
+__device__ __forceinline__ double pmf_mass(const Pmf& x, dd* s_part) { return x.mass >= 0.0 ? x.mass : block_sum(x.p, x.len, s_part); }
 
 // expected mass of a binary operation (reference _pmf.py:96-105) and the rescale that follows it (:80-94)
 __device__ double expected_mass(double m1, double m2) {
     return (is_close(m1, 1.0, 1e-12, 1e-15) && is_close(m2, 1.0, 1e-12, 1e-15)) ? 1.0 : m1 * m2;
 }
-__device__ void rescale(double* p, int n, double expected, dd* s_part) {
-    const double total = block_sum(n, [&](int i) { return p[i]; }, s_part);
-    if (total > 0.0 && !is_close(total, expected, 1e-12, 1e-15)) {
-        const double f = expected / total;
+__device__ double rescale(double* p, int n, double expected, dd* s_part) {  // returns the mass of p afterwards
+    double mass = block_sum(p, n, s_part);
+    if (mass > 0.0 && !is_close(mass, expected, 1e-12, 1e-15)) {
+        const double f = expected / mass;
         for (int i = threadIdx.x; i < n; i += kThreads) p[i] *= f;
+        __syncthreads();
+        mass = block_sum(p, n, s_part);
     }
     __syncthreads();
+    return mass;
 }
 
-// out = a (*) b  (reference DiscretePMF.convolve, _pmf.py:107-125); `a` is `self`
-__device__ void block_convolve(const Pmf& a, const Pmf& b, long long step, double* out, long long* o_start, int* o_len, dd* s_part) {
-    const double ma = block_sum(a.len, [&](int i) { return a.p[i]; }, s_part);
-    const double mb = block_sum(b.len, [&](int i) { return b.p[i]; }, s_part);
+// One output bin of a (*) b: a compensated dot product (Ogita, Rump, Oishi: Dot2).  Every product and every
+// running sum is split into its rounded value and its exact rounding error (TwoProd by FMA, TwoSum); the errors are
+// collected in a second plain sum and added at the end, which gives the result as if computed in twice the working
+// precision and rounded once -- the reference accumulates in 80-bit np.longdouble (_pmf.py:113-118).  Ten fp64
+// operations per term, and the loop-carried chains are one addition each, so four interleaved partial sums keep the
+// fp64 pipe busy (the convolutions are what an event's time consists of, and they run at the pipe's throughput).
+__device__ __forceinline__ void dot2_step(double& sum, double& err, double x, double y) {
+    const double p = __dmul_rn(x, y);
+    const double ep = __fma_rn(x, y, -p);
+    const dd s = two_sum(sum, p);
+    sum = s.hi;
+    err = __dadd_rn(err, __dadd_rn(ep, s.lo));
+}
+__device__ __forceinline__ double convolve_bin(const Pmf& a, const Pmf& b, int k) {
+    const int j0 = max(0, k - (b.len - 1)), j1 = min(k, a.len - 1);
+    double sum[4] = {0.0, 0.0, 0.0, 0.0}, err[4] = {0.0, 0.0, 0.0, 0.0};
+    int j = j0;
+    for (; j + 3 <= j1; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dot2_step(sum[u], err[u], a.p[j + u], b.p[k - j - u]);
+    }
+    for (int u = 0; j <= j1; ++j, ++u) dot2_step(sum[u], err[u], a.p[j], b.p[k - j]);
+    dd t = two_sum(sum[0], sum[1]);
+    double e = __dadd_rn(__dadd_rn(err[0], err[1]), t.lo);
+    const dd t2 = two_sum(sum[2], sum[3]);
+    e = __dadd_rn(e, __dadd_rn(__dadd_rn(err[2], err[3]), t2.lo));
+    const dd t3 = two_sum(t.hi, t2.hi);
+    return __dadd_rn(t3.hi, __dadd_rn(e, t3.lo));
+}
+
+// out = a (*) b  (reference DiscretePMF.convolve, _pmf.py:107-125); `a` is `self`.
+// `shared_bins` != nullptr: the CTAs of a thread-block cluster work on the same event.  The dot products -- the fp64
+// bulk of an event -- are dealt out bin by bin over the cluster's ranks into `shared_bins` (global memory);
+// after a cluster barrier every CTA copies all of them into its own `out` and carries on alone, so everything after
+// the convolution is computed redundantly, bit-identically, by every CTA of the cluster.
+__device__ double block_convolve(const Pmf& a, const Pmf& b, long long step, double* out, long long* o_start, int* o_len, dd* s_part,
+                                 double* shared_bins = nullptr) {  // returns the mass of the result
+    const double ma = pmf_mass(a, s_part);
+    const double mb = pmf_mass(b, s_part);
     int n;
     if (a.len == 1) {
         n = b.len;
@@ -134,67 +213,85 @@ __device__ void block_convolve(const Pmf& a, const Pmf& b, long long step, doubl
         n = a.len;
         const double w = b.p[0];
         for (int k = threadIdx.x; k < n; k += kThreads) out[k] = a.p[k] * w;
+    } else if (shared_bins) {
+        n = a.len + b.len - 1;
+        // bins dealt out one by one: the long dot products sit in the middle of the result, every rank gets its share
+        const int rank = int(cluster_rank()), csize = int(cluster_size());
+        for (int k = rank + csize * int(threadIdx.x); k < n; k += csize * kThreads) shared_bins[k] = convolve_bin(a, b, k);
+        cluster_sync();
+        for (int k = threadIdx.x; k < n; k += kThreads) out[k] = __ldcg(shared_bins + k);
     } else {
         n = a.len + b.len - 1;
-        for (int k = threadIdx.x; k < n; k += kThreads) {
-            const int j0 = max(0, k - (b.len - 1)), j1 = min(k, a.len - 1);
-            // four interleaved double-double accumulators: one dd_add_prod is a chain of nine dependent fp64
-            // operations, a single accumulator would leave the fp64 pipe idle most of the time
-            dd acc0{0.0, 0.0}, acc1{0.0, 0.0}, acc2{0.0, 0.0}, acc3{0.0, 0.0};
-            int j = j0;
-            for (; j + 3 <= j1; j += 4) {
-                acc0 = dd_add_prod(acc0, a.p[j], b.p[k - j]);
-                acc1 = dd_add_prod(acc1, a.p[j + 1], b.p[k - j - 1]);
-                acc2 = dd_add_prod(acc2, a.p[j + 2], b.p[k - j - 2]);
-                acc3 = dd_add_prod(acc3, a.p[j + 3], b.p[k - j - 3]);
-            }
-            for (; j <= j1; ++j) acc0 = dd_add_prod(acc0, a.p[j], b.p[k - j]);
-            out[k] = dd_round(dd_add(dd_add(acc0, acc1), dd_add(acc2, acc3)));
-        }
+        for (int k = threadIdx.x; k < n; k += kThreads) out[k] = convolve_bin(a, b, k);
     }
     *o_start = a.start + b.start;
     *o_len = n;
     __syncthreads();
-    rescale(out, n, expected_mass(ma, mb), s_part);
     (void)step;
+    return rescale(out, n, expected_mass(ma, mb), s_part);
 }
 
-// inclusive prefix sums of x on a grid of n bins (x(i) for bins outside its support is 0), as double-double
-template <typename F>
-__device__ void block_cumsum(int n, F x, double* c_hi, double* c_lo, dd* s_seg) {
+// inclusive prefix sums, as double-double, of TWO functions on a grid of n bins in one pass (one set of barriers, two
+// independent dependency chains): x(i) = src[i - first] for first <= i < first + len, else 0
+struct Window {
+    const double* src;
+    int first, len;
+    double *c_hi, *c_lo;
+    __device__ __forceinline__ double at(int i) const { return (i >= first && i < first + len) ? src[i - first] : 0.0; }
+};
+__device__ void block_cumsum2(int n, const Window& A, const Window& B, dd* s_seg) {
     const int per = (n + kThreads - 1) / kThreads;
     const int i0 = min(n, int(threadIdx.x) * per), i1 = min(n, i0 + per);
-    dd acc{0.0, 0.0};
+    dd acc_a{0.0, 0.0}, acc_b{0.0, 0.0};
     for (int i = i0; i < i1; ++i) {
-        acc = dd_add_d(acc, x(i));
-        c_hi[i] = acc.hi;
-        c_lo[i] = acc.lo;
+        acc_a = dd_add_d(acc_a, A.at(i));
+        acc_b = dd_add_d(acc_b, B.at(i));
+        A.c_hi[i] = acc_a.hi;
+        A.c_lo[i] = acc_a.lo;
+        B.c_hi[i] = acc_b.hi;
+        B.c_lo[i] = acc_b.lo;
     }
     // exclusive scan of the 256 segment totals: shuffles inside a warp, then the eight warp totals
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    dd inc = acc;
+    dd inc_a = acc_a, inc_b = acc_b;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        dd w;
-        w.hi = __shfl_up_sync(0xFFFFFFFFu, inc.hi, o);
-        w.lo = __shfl_up_sync(0xFFFFFFFFu, inc.lo, o);
-        if (lane >= o) inc = dd_add(w, inc);
+        dd wa, wb;
+        wa.hi = __shfl_up_sync(0xFFFFFFFFu, inc_a.hi, o);
+        wa.lo = __shfl_up_sync(0xFFFFFFFFu, inc_a.lo, o);
+        wb.hi = __shfl_up_sync(0xFFFFFFFFu, inc_b.hi, o);
+        wb.lo = __shfl_up_sync(0xFFFFFFFFu, inc_b.lo, o);
+        if (lane >= o) {
+            inc_a = dd_add(wa, inc_a);
+            inc_b = dd_add(wb, inc_b);
+        }
     }
-    dd exc;
-    exc.hi = __shfl_up_sync(0xFFFFFFFFu, inc.hi, 1);
-    exc.lo = __shfl_up_sync(0xFFFFFFFFu, inc.lo, 1);
-    if (lane == 0) exc = dd{0.0, 0.0};
+    dd exc_a, exc_b;
+    exc_a.hi = __shfl_up_sync(0xFFFFFFFFu, inc_a.hi, 1);
+    exc_a.lo = __shfl_up_sync(0xFFFFFFFFu, inc_a.lo, 1);
+    exc_b.hi = __shfl_up_sync(0xFFFFFFFFu, inc_b.hi, 1);
+    exc_b.lo = __shfl_up_sync(0xFFFFFFFFu, inc_b.lo, 1);
+    if (lane == 0) exc_a = exc_b = dd{0.0, 0.0};
     __syncthreads();  // s_seg may still be read by the previous call
-    if (lane == 31) s_seg[warp] = inc;
+    if (lane == 31) {
+        s_seg[warp] = inc_a;
+        s_seg[kThreads / 32 + warp] = inc_b;
+    }
     __syncthreads();
-    dd before{0.0, 0.0};
-    for (int w = 0; w < warp; ++w) before = dd_add(before, s_seg[w]);
-    const dd off = dd_add(before, exc);
+    dd before_a{0.0, 0.0}, before_b{0.0, 0.0};
+    for (int w = 0; w < warp; ++w) {
+        before_a = dd_add(before_a, s_seg[w]);
+        before_b = dd_add(before_b, s_seg[kThreads / 32 + w]);
+    }
+    const dd off_a = dd_add(before_a, exc_a), off_b = dd_add(before_b, exc_b);
     if (threadIdx.x > 0) {
         for (int i = i0; i < i1; ++i) {
-            const dd v = dd_add(off, dd{c_hi[i], c_lo[i]});
-            c_hi[i] = v.hi;
-            c_lo[i] = v.lo;
+            const dd va = dd_add(off_a, dd{A.c_hi[i], A.c_lo[i]});
+            const dd vb = dd_add(off_b, dd{B.c_hi[i], B.c_lo[i]});
+            A.c_hi[i] = va.hi;
+            A.c_lo[i] = va.lo;
+            B.c_hi[i] = vb.hi;
+            B.c_lo[i] = vb.lo;
         }
     }
     __syncthreads();
@@ -202,18 +299,17 @@ __device__ void block_cumsum(int n, F x, double* c_hi, double* c_lo, dd* s_seg) 
 
 // out = max(a, b) of independent variables (reference DiscretePMF.maximum, _pmf.py:127-148); `a` is `self`.
 // c[0..3]: four scratch arrays of the union length
-__device__ void block_maximum(const Pmf& a, const Pmf& b, long long step, double* out, long long* o_start, int* o_len,
-                              double* const* c, dd* s_part, dd* s_seg) {
-    const double ma = block_sum(a.len, [&](int i) { return a.p[i]; }, s_part);
-    const double mb = block_sum(b.len, [&](int i) { return b.p[i]; }, s_part);
+__device__ double block_maximum(const Pmf& a, const Pmf& b, long long step, double* out, long long* o_start, int* o_len,
+                                double* const* c, dd* s_part, dd* s_seg) {  // returns the mass of the result
+    const double ma = pmf_mass(a, s_part);
+    const double mb = pmf_mass(b, s_part);
     const long long lo = min(a.start, b.start);
     const long long hi = max(a.start + (long long)(a.len - 1) * step, b.start + (long long)(b.len - 1) * step);
     const int n = int((hi - lo) / step) + 1;
     const int oa = int((a.start - lo) / step), ob = int((b.start - lo) / step);
     auto pa = [&](int i) { return (i >= oa && i < oa + a.len) ? a.p[i - oa] : 0.0; };
     auto pb = [&](int i) { return (i >= ob && i < ob + b.len) ? b.p[i - ob] : 0.0; };
-    block_cumsum(n, pa, c[0], c[1], s_seg);
-    block_cumsum(n, pb, c[2], c[3], s_seg);
+    block_cumsum2(n, Window{a.p, oa, a.len, c[0], c[1]}, Window{b.p, ob, b.len, c[2], c[3]}, s_seg);
     for (int i = threadIdx.x; i < n; i += kThreads) {
         // p_a(i) F_b(i) + p_b(i) F_a(i - 1), in double-double, rounded once
         dd t = dd_mul_d(dd{c[2][i], c[3][i]}, pa(i));
@@ -223,7 +319,7 @@ __device__ void block_maximum(const Pmf& a, const Pmf& b, long long step, double
     *o_start = lo;
     *o_len = n;
     __syncthreads();
-    rescale(out, n, expected_mass(ma, mb), s_part);
+    return rescale(out, n, expected_mass(ma, mb), s_part);
 }
 
 enum { kRuleTruncate = 1, kRuleRemove = 2, kRuleRedistribute = 3 };
@@ -232,7 +328,7 @@ enum { kClipOk = 0, kClipNoLowerBin = 1, kClipNoUpperBin = 2, kClipEmpty = 3, kC
 // Clip r to [min_value, max_value] and apply the flow rules (reference _convert_to_simulated_event,
 // _propagator.py:158-265).  `out` has room for the kept bins (at least one).  Returns a kClip* status (block-uniform).
 __device__ int block_clip(const Pmf& r, long long step, long long min_value, long long max_value, int under_rule, int over_rule,
-                          double* out, long long* o_start, int* o_len, double* o_under, double* o_over, dd* s_part) {
+                          double* out, long long* o_start, int* o_len, double* o_under, double* o_over, double* o_mass, dd* s_part) {
     if (min_value > max_value) return kClipBadBounds;
     // kept bins: values in [min_value, max_value]; bins below / above are contiguous runs (values ascend)
     long long k0 = min_value - r.start, k1 = max_value - r.start;
@@ -241,8 +337,8 @@ __device__ int block_clip(const Pmf& r, long long step, long long min_value, lon
     const long long len_ll = r.len;
     const int first = int(k0 < len_ll ? k0 : len_ll), last = int(k1 < len_ll - 1 ? k1 : len_ll - 1);
     int n = max(0, last - first + 1);
-    double under = block_sum(first, [&](int i) { return r.p[i]; }, s_part);
-    double over = block_sum(r.len - 1 - last, [&](int i) { return r.p[last + 1 + i]; }, s_part);
+    double under, over;
+    block_sum2(r.p, first, r.p + last + 1, r.len - 1 - last, s_part, &under, &over);
     for (int i = threadIdx.x; i < n; i += kThreads) out[i] = r.p[first + i];
     long long start = r.start + (long long)first * step;
     __syncthreads();
@@ -280,7 +376,7 @@ __device__ int block_clip(const Pmf& r, long long step, long long min_value, lon
     }
     __syncthreads();
     if (redistribute > 0.0) {
-        const double inside = block_sum(n, [&](int i) { return out[i]; }, s_part);
+        const double inside = block_sum(out, n, s_part);
         if (inside == 0.0) {
             if (threadIdx.x == 0) out[0] = redistribute;
             n = 1;
@@ -293,7 +389,7 @@ __device__ int block_clip(const Pmf& r, long long step, long long min_value, lon
     if (n == 0) return kClipEmpty;
     const double lost = under + over;
     const double target = fmax(0.0, 1.0 - lost);
-    const double inside = block_sum(n, [&](int i) { return out[i]; }, s_part);
+    const double inside = block_sum(out, n, s_part);
     if (inside > 0.0) {
         for (int i = threadIdx.x; i < n; i += kThreads) out[i] = out[i] / inside * target;
     } else if (target > 0.0) {
@@ -302,12 +398,15 @@ __device__ int block_clip(const Pmf& r, long long step, long long min_value, lon
         start = min_value;
     }
     __syncthreads();
-    const double total = block_sum(n, [&](int i) { return out[i]; }, s_part) + under + over;
+    double mass = block_sum(out, n, s_part);
+    const double total = mass + under + over;
     if (!is_close(total, 1.0, 1e-12, 1e-15) && total > 0.0) {
         const double corr = 1.0 / total;
         for (int i = threadIdx.x; i < n; i += kThreads) out[i] *= corr;
         __syncthreads();
+        mass = block_sum(out, n, s_part);
     }
+    *o_mass = mass;
     *o_start = start;
     *o_len = n;
     *o_under = under;
@@ -326,6 +425,8 @@ struct AnalyticParams {
     const long long* pmf_start;
     const int64_t* pmf_off;    // [n_pmfs + 1]
     const double* pmf_probs;
+    const double* pmf_mass;    // [n_pmfs] block_sum of each activity PMF (pmf_mass_kernel)
+    double* out_mass;          // [E] mass of each event's result
     long long* out_start;      // [E]
     int32_t* out_len;          // [E]
     const int64_t* out_off;    // [E + 1] slot of each event in out_probs
@@ -335,21 +436,34 @@ struct AnalyticParams {
     int32_t* status;           // [E]
     double* scratch;           // per CTA: 7 arrays of scratch_len (null: they fit the CTA's dynamic shared memory)
     long long scratch_len;
+    double* cluster_bins;      // per cluster: 2 arrays of scratch_len, the bins of a convolution dealt out over its CTAs
     long long step;
     int under_rule, over_rule;
 };
 
+// mass of every activity PMF, once per run
+__global__ void __launch_bounds__(kThreads) pmf_mass_kernel(const int64_t* pmf_off, const double* pmf_probs, double* pmf_mass) {
+    __shared__ dd s_part[2 * (kThreads / 32)];
+    const int a = blockIdx.x;
+    const double m = block_sum(pmf_probs + pmf_off[a], int(pmf_off[a + 1] - pmf_off[a]), s_part);
+    if (threadIdx.x == 0) pmf_mass[a] = m;
+}
+
 __global__ void __launch_bounds__(kThreads) analytic_level_kernel(const AnalyticParams p, int pos0) {
-    __shared__ dd s_part[kThreads / 32];
+    __shared__ dd s_part[2 * (kThreads / 32)];
     __shared__ dd s_seg[kThreads];
     __shared__ long long s_start[2];
     __shared__ int s_len[2];
-    const int ev = p.order[pos0 + blockIdx.x];
+    // one event per thread-block cluster (a narrow level is launched with 2, 4 or 8 CTAs per event, a wide one with 1)
+    const unsigned csize = cluster_size(), slot = blockIdx.x / csize;
+    const bool lead = cluster_rank() == 0;
+    const int ev = p.order[pos0 + slot];
     const int64_t b = p.pred_off[ev], e = p.pred_off[ev + 1];
     double* const out = p.out_probs + p.out_off[ev];
     if (b == e) {  // origin: a unit mass at the rounded earliest time (_propagator.py:103-110)
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 0 && lead) {
             out[0] = 1.0;
+            p.out_mass[ev] = 1.0;
             p.out_start[ev] = p.origin[ev];
             p.out_len[ev] = 1;
             p.underflow[ev] = 0.0;
@@ -362,37 +476,43 @@ __global__ void __launch_bounds__(kThreads) analytic_level_kernel(const Analytic
     // through them between two barriers), else in a global scratch slab
     extern __shared__ double s_scratch[];
     double* const base = p.scratch ? p.scratch + size_t(blockIdx.x) * 7 * size_t(p.scratch_len) : s_scratch;
+    // two buffers in turn: a CTA that is ahead writes the bins of predecessor k + 1 while another still copies those of k;
+    // it cannot reach k + 2 before the barrier of k + 1, which every CTA passes only after its copy of k
+    double* const cbins = csize > 1 ? p.cluster_bins + size_t(slot) * 2 * size_t(p.scratch_len) : nullptr;
     double* conv = base;
     double* run = base + p.scratch_len;
     double* tmp = base + 2 * p.scratch_len;
     double* const c[4] = {base + 3 * p.scratch_len, base + 4 * p.scratch_len, base + 5 * p.scratch_len, base + 6 * p.scratch_len};
-    Pmf r{0, 0, nullptr};
+    Pmf r{0, 0, nullptr, -1.0};
     for (int64_t k = b; k < e; ++k) {
         const int src = p.pred_src[k], a = p.pred_pmf[k];
-        const Pmf pred{p.out_start[src], p.out_len[src], p.out_probs + p.out_off[src]};
-        const Pmf act{p.pmf_start[a], int(p.pmf_off[a + 1] - p.pmf_off[a]), p.pmf_probs + p.pmf_off[a]};
+        const Pmf pred{p.out_start[src], p.out_len[src], p.out_probs + p.out_off[src], p.out_mass[src]};
+        const Pmf act{p.pmf_start[a], int(p.pmf_off[a + 1] - p.pmf_off[a]), p.pmf_probs + p.pmf_off[a], p.pmf_mass[a]};
         double* const dst = (k == b) ? run : conv;
-        block_convolve(pred, act, p.step, dst, &s_start[0], &s_len[0], s_part);  // every thread writes the same values
+        const double cv_mass = block_convolve(pred, act, p.step, dst, &s_start[0], &s_len[0], s_part,  // every thread writes the same values
+                                              cbins ? cbins + size_t((k - b) & 1) * size_t(p.scratch_len) : nullptr);
         __syncthreads();
-        const Pmf cv{s_start[0], s_len[0], dst};
+        const Pmf cv{s_start[0], s_len[0], dst, cv_mass};
         if (k == b) {
             r = cv;
         } else {
-            block_maximum(r, cv, p.step, tmp, &s_start[1], &s_len[1], c, s_part, s_seg);
+            const double mx_mass = block_maximum(r, cv, p.step, tmp, &s_start[1], &s_len[1], c, s_part, s_seg);
             __syncthreads();
-            r = Pmf{s_start[1], s_len[1], tmp};
+            r = Pmf{s_start[1], s_len[1], tmp, mx_mass};
             double* t = run;  // the result becomes the running PMF
             run = tmp;
             tmp = t;
         }
         __syncthreads();
     }
+    if (!lead) return;  // the event's result is written once (no cluster barrier follows)
     long long o_start = 0;
     int o_len = 0;
-    double under = 0.0, over = 0.0;
-    const int st = block_clip(r, p.step, p.lower[ev], p.upper[ev], p.under_rule, p.over_rule, out, &o_start, &o_len, &under, &over, s_part);
+    double under = 0.0, over = 0.0, mass = 0.0;
+    const int st = block_clip(r, p.step, p.lower[ev], p.upper[ev], p.under_rule, p.over_rule, out, &o_start, &o_len, &under, &over, &mass, s_part);
     if (threadIdx.x == 0) {
         p.status[ev] = st;
+        p.out_mass[ev] = mass;
         p.out_start[ev] = o_start;
         p.out_len[ev] = o_len;
         p.underflow[ev] = under;
@@ -414,7 +534,7 @@ struct OpParams {
     int32_t* o_status;
 };
 __global__ void __launch_bounds__(kThreads) pmf_op_kernel(const OpParams p, int op) {
-    __shared__ dd s_part[kThreads / 32];
+    __shared__ dd s_part[2 * (kThreads / 32)];
     __shared__ dd s_seg[kThreads];
     long long o_start = 0;
     int o_len = 0, st = kClipOk;
@@ -425,7 +545,8 @@ __global__ void __launch_bounds__(kThreads) pmf_op_kernel(const OpParams p, int 
         double* const c[4] = {p.scratch, p.scratch + p.scratch_len, p.scratch + 2 * p.scratch_len, p.scratch + 3 * p.scratch_len};
         block_maximum(p.a, p.b, p.step, p.out, &o_start, &o_len, c, s_part, s_seg);
     } else {
-        st = block_clip(p.a, p.step, p.min_value, p.max_value, p.under_rule, p.over_rule, p.out, &o_start, &o_len, &under, &over, s_part);
+        double mass = 0.0;
+        st = block_clip(p.a, p.step, p.min_value, p.max_value, p.under_rule, p.over_rule, p.out, &o_start, &o_len, &under, &over, &mass, s_part);
     }
     if (threadIdx.x == 0) {
         *p.o_start = o_start;
@@ -616,6 +737,7 @@ int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* 
         int32_t *d_pred_src = nullptr, *d_pred_pmf = nullptr, *d_out_len = nullptr, *d_status = nullptr;
         long long *d_lower = nullptr, *d_upper = nullptr, *d_origin = nullptr, *d_pmf_start = nullptr, *d_out_start = nullptr;
         double *d_pmf_probs = nullptr, *d_out_probs = nullptr, *d_under = nullptr, *d_over = nullptr, *d_scratch = nullptr;
+        double *d_cluster_bins = nullptr, *d_out_mass = nullptr, *d_pmf_mass = nullptr;
         std::vector<int32_t> status(static_cast<size_t>(E));
         static_assert(sizeof(long long) == sizeof(int64_t), "64-bit values");
         ACUDA(mem.upload(&d_order, order.data(), order.size()));
@@ -633,17 +755,23 @@ int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* 
         ACUDA(mem.alloc(&d_out_len, size_t(E)));
         ACUDA(mem.alloc(&d_status, size_t(E)));
         ACUDA(mem.alloc(&d_out_probs, size_t(cap)));
+        ACUDA(mem.alloc(&d_out_mass, size_t(E)));
+        ACUDA(mem.alloc(&d_pmf_mass, size_t(std::max(d->n_pmfs, 1))));
         ACUDA(mem.alloc(&d_under, size_t(E)));
         ACUDA(mem.alloc(&d_over, size_t(E)));
         const size_t smem_need = size_t(7) * size_t(scratch_len) * sizeof(double);
         int smem_max = 0;
         ACUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         const bool in_smem = smem_need + 8192 <= size_t(smem_max);  // static shared memory of the kernel is below 8 KB
+        int sm_count = 1;
+        ACUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
         if (in_smem) {
             ACUDA(cudaFuncSetAttribute(analytic_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem_need)));
-        } else {
-            ACUDA(mem.alloc(&d_scratch, size_t(max_width) * 7 * size_t(scratch_len)));
+        } else {  // one slab per CTA of the largest launch (a clustered launch has at most sm_count CTAs)
+            ACUDA(mem.alloc(&d_scratch, size_t(std::max<int64_t>(max_width, sm_count)) * 7 * size_t(scratch_len)));
         }
+        // levels narrower than the machine: 2, 4 or 8 CTAs per event share its convolutions (at most sm_count / 2 clusters)
+        ACUDA(mem.alloc(&d_cluster_bins, size_t(std::max(sm_count / 2, 1)) * 2 * size_t(scratch_len)));
         ACUDA(cudaMemset(d_out_probs, 0, size_t(std::max<int64_t>(cap, 1)) * 8));
         p.order = d_order;
         p.pred_off = d_pred_off;
@@ -655,6 +783,8 @@ int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* 
         p.pmf_start = d_pmf_start;
         p.pmf_off = d_pmf_off;
         p.pmf_probs = d_pmf_probs;
+        p.pmf_mass = d_pmf_mass;
+        p.out_mass = d_out_mass;
         p.out_start = d_out_start;
         p.out_len = d_out_len;
         p.out_off = d_out_off;
@@ -664,17 +794,32 @@ int32_t mcdp_analytic_run(const mcdp_analytic_desc* d, int32_t device, int64_t* 
         p.status = d_status;
         p.scratch = d_scratch;
         p.scratch_len = scratch_len;
+        p.cluster_bins = d_cluster_bins;
         p.step = d->step;
         p.under_rule = d->underflow_rule;
         p.over_rule = d->overflow_rule;
         ACUDA(cudaDeviceSynchronize());
         g_profile[1] = ms_since(t_phase);  // device allocations and uploads
         t_phase = std::chrono::steady_clock::now();
+        if (d->n_pmfs > 0) {
+            pmf_mass_kernel<<<unsigned(d->n_pmfs), kThreads>>>(d_pmf_off, d_pmf_probs, d_pmf_mass);
+            ACUDA(cudaGetLastError());
+        }
         for (size_t l = 0; l + 1 < level_begin.size(); ++l) {
             const int n = level_begin[l + 1] - level_begin[l];
             if (n <= 0) continue;
-            analytic_level_kernel<<<unsigned(n), kThreads, in_smem ? smem_need : 0>>>(p, level_begin[l]);
-            ACUDA(cudaGetLastError());
+            const int csize = n * 8 <= sm_count ? 8 : (n * 4 <= sm_count ? 4 : (n * 2 <= sm_count ? 2 : 1));
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(unsigned(n * csize));
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = in_smem ? smem_need : 0;
+            cudaLaunchAttribute attr{};
+            attr.id = cudaLaunchAttributeClusterDimension;
+            attr.val.clusterDim.x = unsigned(csize);
+            attr.val.clusterDim.y = attr.val.clusterDim.z = 1;
+            cfg.attrs = &attr;
+            cfg.numAttrs = 1;
+            ACUDA(cudaLaunchKernelEx(&cfg, analytic_level_kernel, p, int(level_begin[l])));
         }
         ACUDA(cudaDeviceSynchronize());
         g_profile[2] = ms_since(t_phase);  // one launch per level, all levels
@@ -739,8 +884,8 @@ int32_t mcdp_pmf_op(int32_t op, int32_t device, int64_t step, int64_t a_start, i
         ACUDA(mem.alloc(&d_start, 1));
         ACUDA(mem.alloc(&d_len, 1));
         ACUDA(mem.alloc(&d_status, 1));
-        p.a = Pmf{a_start, a_len, d_a};
-        p.b = Pmf{b_start, b_len, d_b};
+        p.a = Pmf{a_start, a_len, d_a, -1.0};
+        p.b = Pmf{b_start, b_len, d_b, -1.0};
         p.step = st;
         p.min_value = min_value;
         p.max_value = max_value;

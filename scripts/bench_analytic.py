@@ -31,6 +31,10 @@ def main():
         create = ns.create_analytic_propagator
     else:
         sys.path.insert(0, ROOT)
+        if os.environ.get("MCDP_LIB"):  # scratch A/B builds (scripts/ab_variants.sh)
+            from mc_dagprop_b200 import capi
+
+            capi.LIB_PATH = os.path.abspath(os.environ["MCDP_LIB"])
         import mc_dagprop
         import mc_dagprop.analytic as an
 
