@@ -7,7 +7,7 @@ underflow / overflow rules.  The names exported here are those of the reference'
 (``analytic/__init__.py``); the arithmetic behind them runs on the GPU (``csrc/mcdp_analytic.cu``):
 
 ======================================  ====================================================================
-``DiscretePMF.convolve`` / ``maximum``   one device call each (``mcdp_pmf_op``), double-double accumulation
+``DiscretePMF.convolve`` / ``maximum``   one device call each (``mcdp_pmf_op``), compensated (twice-working-precision) accumulation
 ``AnalyticPropagator.run``               ONE device call for the whole DAG (``mcdp_analytic_run``): a launch per
                                          topological level, a CTA per event
 ``create_analytic_propagator``           host side: validation (``_validate.py``) and topological order

@@ -1,7 +1,7 @@
 """``DiscretePMF``: a probability mass function on an equidistant grid (reference ``analytic/_pmf.py``).
 
 Same fields, checks and methods as the reference class; ``convolve`` and ``maximum`` run on the GPU
-(``mcdp_pmf_op``, double-double accumulation in place of the reference's ``np.longdouble``) and apply the reference's
+(``mcdp_pmf_op``, compensated twice-working-precision accumulation in place of the reference's ``np.longdouble``) and apply the reference's
 mass correction (``_expected_mass`` / ``_rescale``, ``_pmf.py:80-105``) there.
 """
 from __future__ import annotations

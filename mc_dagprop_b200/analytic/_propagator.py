@@ -3,7 +3,7 @@
 
 ``run()`` flattens the context into arrays -- integer bounds of every event, the precedence list, one PMF per
 edge -- and makes ONE call into the library (``mcdp_analytic_run``): a kernel launch per topological level, a CTA per
-event, convolution / maximum / bound handling block-cooperative in double-double arithmetic.  The result comes back
+event, convolution / maximum / bound handling block-cooperative in compensated (twice-working-precision) arithmetic.  The result comes back
 as one packed array of bins that is sliced into the reference's ``SimulatedEvent`` objects.
 """
 from __future__ import annotations
