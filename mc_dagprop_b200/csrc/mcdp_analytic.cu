@@ -8,17 +8,20 @@
 // An event with predecessors takes  max_i (PMF(src_i) (*) PMF(activity_i)),  clipped to its [earliest, latest]
 // window with the context's underflow / overflow rules.
 //
-// Mapping: events of one topological level are independent -> one CTA per event, one launch per level.  Inside a
-// CTA the three operations are block-cooperative:
-//   * convolution: thread k owns output bins k, k + 256, ...; each bin is a dot product accumulated in
-//     double-double (TwoProd via FMA + TwoSum) and rounded once -- the reference accumulates in 80-bit
-//     np.longdouble and casts to float64; both are within an ulp of the exactly rounded sum;
+// Mapping: events of one topological level are independent -> one launch per level, one CTA per event -- or, when the
+// level is narrower than the machine, a thread-block cluster of 2, 4 or 8 CTAs per event that shares the event's
+// convolutions.  Inside a CTA the three operations are block-cooperative:
+//   * convolution: thread k owns output bins k, k + 256, ...; each bin is a compensated dot product (Dot2: TwoProd via
+//     FMA + TwoSum, the rounding errors summed separately, added once at the end) -- the reference accumulates in
+//     80-bit np.longdouble and casts to float64; both are within an ulp of the exactly rounded sum;
 //   * maximum of two independent variables: P(max = x) = p_a(x) F_b(x) + p_b(x) F_a(x - 1) on the union grid, the two
-//     CDFs by a block-wide double-double prefix sum (per-thread segments + one scan of the 256 segment totals);
+//     CDFs by one block-wide double-double prefix-sum pass (per-thread segments + a shuffle scan of the segment totals);
 //   * the mass corrections of the reference (`_rescale`, the clip-and-normalise of `_convert_to_simulated_event`)
-//     are block reductions in double-double followed by the same compare-and-scale steps.
-// PMFs live in global memory (L2-resident at these sizes): a per-CTA scratch of seven arrays as long as the widest
-// intermediate window, sized by the host from the event bounds.
+//     are block reductions in double-double followed by the same compare-and-scale steps; the mass of a PMF is
+//     computed where it is produced and travels with it.
+// Inputs and results live in global memory (L2-resident at these sizes); the intermediates of an event -- seven
+// arrays as long as the widest window, sized by the host from the event bounds -- in the CTA's shared memory when
+// they fit, else in a global slab.
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
 
