@@ -120,20 +120,28 @@ class AnalyticPropagator:
         step = self.context.step
         start, length, off, probs, under, over = _device.analytic_run(
             *self._flatten(), int(self.underflow_rule), int(self.overflow_rule))
+        n = len(length)
+        if n == 0:
+            return ()
+        # results packed back to back (`off` are the result slots, sized from the event bounds, usually longer than the
+        # results) and the value grids of all events in one array; both are sliced per event below
+        vend = np.cumsum(length, dtype=np.int64)
+        vbeg = vend - length
+        within = np.arange(int(vend[-1]), dtype=np.int64) - np.repeat(vbeg, length)
+        if int(off[-1]) != int(vend[-1]):
+            probs = probs[np.repeat(off[:-1], length) + within]
+        values = np.repeat(start.astype(float), length) + float(step) * within.astype(float)
         # the checks of the reference's DiscretePMF constructor (_pmf.py:38-52) for all events at once: the grids are
         # ascending by construction, every event has at least one bin, what is left to check is the mass
-        n = len(length)
-        if n:
-            mass = np.add.reduceat(probs, off[:-1]) if probs.size else np.zeros(n)
-            if np.any((mass > 1.0) & ~np.isclose(mass, 1.0)):
-                raise ValueError("Probabilities must sum to <= 1.0")
-        grid = np.arange(int(length.max()) if n else 0, dtype=float) * float(step)
+        mass = np.add.reduceat(probs, vbeg)
+        if np.any((mass > 1.0) & ~np.isclose(mass, 1.0)):
+            raise ValueError("Probabilities must sum to <= 1.0")
+        begs, ends, unders, overs = vbeg.tolist(), vend.tolist(), under.tolist(), over.tolist()  # Python scalars in the loop
+        unchecked = DiscretePMF._unchecked
         out = []
         for i in range(n):
-            k = int(length[i])
-            o = int(off[i])
-            pmf = DiscretePMF._unchecked(float(start[i]) + grid[:k], probs[o:o + k], step)
-            out.append(SimulatedEvent(pmf, ProbabilityMass(under[i]), ProbabilityMass(over[i])))
+            v, e = begs[i], ends[i]
+            out.append(SimulatedEvent(unchecked(values[v:e], probs[v:e], step), unders[i], overs[i]))
         return tuple(out)
 
     def _convert_to_simulated_event(self, pmf: DiscretePMF, min_value: int, max_value: int) -> SimulatedEvent:

@@ -87,3 +87,58 @@ def test_package_surface_matches_reference():
     assert [int(r) for r in analytic.UnderflowRule] == [1, 2, 3] and analytic.OverflowRule.REDISTRIBUTE == 3
     from mc_dagprop.analytic._context import AnalyticActivity, SimulatedEvent  # noqa: F401  (paths the reference's tests import)
     from mc_dagprop.analytic._pmf import DiscretePMF  # noqa: F401
+
+
+@pytest.mark.parametrize("slack", [True, False])
+def test_run_unpacks_the_device_result(monkeypatch, slack):
+    """``AnalyticPropagator.run`` around a stand-in for the device call: result slots longer than the results, value
+    grids from start / step, the bulk mass check of the reference's ``DiscretePMF`` constructor."""
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import types
+
+    import analytic_cases as ac
+    import mc_dagprop
+    import mc_dagprop.analytic as an
+    from mc_dagprop_b200.analytic import _device
+
+    ns = types.SimpleNamespace(Event=mc_dagprop.Event, EventTimestamp=mc_dagprop.EventTimestamp, DiscretePMF=an.DiscretePMF,
+                               AnalyticActivity=an.AnalyticActivity, AnalyticContext=an.AnalyticContext,
+                               UnderflowRule=an.UnderflowRule, OverflowRule=an.OverflowRule)
+    ctx = ac.build_context(ns, "dag", 120, 3, 5, None, 1, 1)
+    rng = np.random.default_rng(0)
+    sent = {}
+
+    def fake_run(lower, upper, origin, step, *rest):
+        n = len(lower)
+        length = rng.integers(1, 30, n).astype(np.int32)
+        slots = length + (rng.integers(0, 4, n) if slack else 0)
+        off = np.concatenate([[0], np.cumsum(slots)]).astype(np.int64)
+        probs = rng.random(int(off[-1])) + 5.0  # whatever lies in the unused tail of a slot must not be looked at
+        for i in range(n):
+            seg = probs[off[i]: off[i] + length[i]]
+            seg /= seg.sum() * (1.0 + 1e-9)
+        under = rng.random(n) * 1e-3
+        sent.update(start=np.asarray(lower), length=length, off=off, probs=probs.copy(), under=under, step=step)
+        return np.asarray(lower), length, off, probs, under, np.zeros(n)
+
+    monkeypatch.setattr(_device, "analytic_run", fake_run)
+    prop = an.create_analytic_propagator(ctx)
+    res = prop.run()
+    assert len(res) == len(ctx.events) and sent["step"] == 5
+    for i, r in enumerate(res):
+        k, o = int(sent["length"][i]), int(sent["off"][i])
+        assert np.array_equal(r.pmf.probabilities, sent["probs"][o:o + k])
+        assert np.array_equal(r.pmf.values, float(sent["start"][i]) + 5.0 * np.arange(k))
+        assert r.pmf.step == 5 and float(r.underflow) == sent["under"][i] and float(r.overflow) == 0.0
+        r.pmf.validate()
+    # a result whose mass exceeds one is refused like the reference's constructor refuses it
+    def too_heavy(*args):
+        out = list(fake_run(*args))
+        out[3][int(out[2][7]): int(out[2][7]) + int(out[1][7])] *= 1.5
+        return tuple(out)
+
+    monkeypatch.setattr(_device, "analytic_run", too_heavy)
+    with pytest.raises(ValueError, match="sum to <= 1.0"):
+        prop.run()
