@@ -28,9 +28,10 @@
 extern "C" {
 #endif
 
-#define MCDP_ABI_VERSION 4 /* 2: + mcdp_run_attribution_device / _host; 3: + mcdp_plan_launch_shape,
+#define MCDP_ABI_VERSION 5 /* 2: + mcdp_run_attribution_device / _host; 3: + mcdp_plan_launch_shape,
                               MCDP_OPT_SAMPLES_PER_LANE (both additive); 4: + MCDP_OPT_CLUSTER_SIZE, mcdp_planset_*,
-                              launch_shape slot 6 reports the cluster size (generator contract mcdp-philox-v2) */
+                              launch_shape slot 6 reports the cluster size (generator contract mcdp-philox-v2);
+                              5: + MCDP_OPT_SMALL_CALL_MAX, mcdp_analytic_last_profile (both additive) */
 
 enum {
     MCDP_OK = 0,
@@ -112,8 +113,12 @@ enum {
     MCDP_OPT_SAMPLES_PER_LANE = 5, /* samples a lane owns in the sweep kernel: 2 = 64-sample groups at 64 registers,
                                      4 = 128-sample groups at 96 registers with 256-bit row accesses (needs 32-byte
                                      aligned buffers, else falls back to 2); 0 = auto.  Results do not depend on it. */
-    MCDP_OPT_CLUSTER_SIZE = 6      /* quad kernel, launches with fewer sample groups than SMs: CTAs per thread-block
+    MCDP_OPT_CLUSTER_SIZE = 6,     /* quad kernel, launches with fewer sample groups than SMs: CTAs per thread-block
                                      cluster that share one group and split its levels (2, 4, 8); 1 = never; 0 = auto.
+                                     Results do not depend on it. */
+    MCDP_OPT_SMALL_CALL_MAX = 7    /* full-output and injected calls of at most this many samples (run(seed),
+                                     _core.cpp:312-353) take the two-kernel path of mcdp_small_sweep.cuh: one thread per
+                                     activity draws, one thread per event propagates.  -1 = auto (default), 0 = never.
                                      Results do not depend on it. */
 };
 

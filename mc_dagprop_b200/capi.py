@@ -19,6 +19,7 @@ MCDP_OK, MCDP_ERR_INVALID, MCDP_ERR_CUDA, MCDP_ERR_ARG = 0, 1, 2, 3
 DEVICE_NONE = -1
 OPT_STREAM_KEY, OPT_WARPS_PER_GROUP, OPT_GROUPS_PER_CTA, OPT_HOST_CHUNK, OPT_RNG_STREAM, OPT_SAMPLES_PER_LANE = 0, 1, 2, 3, 4, 5
 OPT_CLUSTER_SIZE = 6
+OPT_SMALL_CALL_MAX = 7
 RNG_PHILOX, RNG_REFERENCE = 0, 1
 MAX_THRESHOLDS = 4
 CHUNK_UNITS = 16

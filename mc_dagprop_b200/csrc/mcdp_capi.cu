@@ -21,6 +21,7 @@
 #include "mcdp_compat.cuh"
 #include "mcdp_chunk_sweep.cuh"
 #include "mcdp_quad_sweep.cuh"
+#include "mcdp_small_sweep.cuh"
 
 using namespace mcdp;
 
@@ -163,6 +164,18 @@ struct mcdp_plan {
     int rng_stream = 0;  // 0 Philox contract, 1 reference-compatible Xoshiro stream
     DevBuf<ActRec> d_acts;
     DevBuf<double> d_norm_cache;
+    // calls of a handful of samples (mcdp_small_sweep.cuh): the evaluation-ordered records themselves and one sampling
+    // record per activity index, uploaded on first use
+    struct SmallDev {
+        DevBuf<EventRec> events;
+        DevBuf<PredRec> items;
+        DevBuf<uint32_t> pred_src, pred_act;
+        DevBuf<int4> tiles;
+        int32_t n_items = 0, n_tiles = 0;
+        cudaMemPool_t pool = nullptr;  // stream-ordered scratch of the calls ([samples][precedence entries] durations)
+        bool ready = false, unsupported = false;
+    } small;
+    int64_t small_max = -1;  // calls of at most this many samples take that path; -1 auto, 0 never
     // host-call workspaces
     HostSlot slots[2];
     DevBuf<double> d_stat_f64;
@@ -241,6 +254,12 @@ mcdp_plan::~mcdp_plan() {
         d_scratch.release();
         d_acts.release();
         d_norm_cache.release();
+        small.events.release();
+        small.items.release();
+        small.pred_src.release();
+        small.pred_act.release();
+        small.tiles.release();
+        if (small.pool) cudaMemPoolDestroy(small.pool);
         d_stat_f64.release();
         d_stat_u64.release();
         d_stat_u32.release();
@@ -556,6 +575,153 @@ int32_t ensure_chunk_stream(mcdp_plan* plan, bool reduced, bool dense, SweepPara
 
 int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// ---- calls of a handful of samples (mcdp_small_sweep.cuh) ----
+// Measured (profiles/r02_small_calls.txt): one CTA per sample, so up to a sample per SM the time grows slowly with the
+// number of samples -- 100k-event DAG 0.86 ms for one sample, 1.5 ms for 64, against 4.4 ms of the quad kernel's
+// cluster launch for anything up to 128; 1M-event DAG 6.9 ms against 35 ms; 50k-event chain 53 against 86 ms.  The
+// sweep kernels' throughput wins from 100-250 samples on, the rule stays well below that.
+constexpr int64_t kSmallAutoMax = 64;
+constexpr int64_t kSmallScratchMax = int64_t(1) << 30;  // bytes of [samples][precedence entries] durations per call
+bool use_small(const mcdp_plan* plan, int64_t n) {
+    if (n <= 0 || n > 65535 || plan->small.unsupported || plan->host.max_fan_in > kSmallTilePreds) return false;
+    if (plan->host.P * n * 8 > kSmallScratchMax && plan->small_max < 0) return false;
+    if (plan->small_max >= 0) return n <= plan->small_max;
+    // an explicit kernel choice (samples per lane, cluster size, warps per group) is a request for the sweep kernels
+    if (plan->samples_per_lane || plan->cluster_size || plan->warps_per_group || plan->groups_per_cta) return false;
+    return n <= std::min<int64_t>(kSmallAutoMax, plan->sm_count);
+}
+
+int32_t ensure_small(mcdp_plan* plan) {
+    std::lock_guard<std::mutex> lock(plan->stream_mu);
+    if (plan->small.ready) return MCDP_OK;
+    const HostPlan& h = plan->host;
+    // sampling records: every precedence entry (with its position) and every orphan activity, by sampler class --
+    // the gamma samplers vote across the warp, so Marsaglia-Tsang and the exact transformation get warps of their own
+    std::vector<PredRec> by_class[3];
+    auto add = [&](PredRec r, uint32_t pos) {
+        r.next_src_row = pos;
+        int cls = 0;
+        if ((r.meta >> 29) == uint32_t(MCDP_DIST_GAMMA)) cls = (h.dists[r.dist].flags & 8) ? 2 : 1;
+        by_class[cls].push_back(r);
+    };
+    std::vector<uint32_t> src(h.preds.size()), act(h.preds.size());
+    for (size_t j = 0; j < h.preds.size(); ++j) {
+        add(h.preds[j], uint32_t(j));
+        src[j] = h.preds[j].src_row;
+        act[j] = h.preds[j].act;
+    }
+    for (const PredRec& r : h.orphans) add(r, kSmallNoPos);
+    std::vector<PredRec> items;
+    for (auto& v : by_class) {
+        while (v.size() % 32) v.push_back(v.back());  // whole warps per class; the copy writes the same values again
+        items.insert(items.end(), v.begin(), v.end());
+    }
+    // tiles: events of one level, bounded in events and in precedence entries
+    std::vector<int4> tiles;
+    for (int32_t l = 0; l < h.n_levels; ++l) {
+        int32_t pos = h.level_begin[l];
+        const int32_t end = h.level_begin[l + 1];
+        while (pos < end) {
+            int4 t = make_int4(pos, 0, int(h.events[size_t(pos)].pred_begin), 0);
+            while (pos < end && t.y < kSmallTileEvents && t.w + int(h.events[size_t(pos)].fan_in) <= kSmallTilePreds) {
+                t.w += int(h.events[size_t(pos)].fan_in);
+                ++t.y;
+                ++pos;
+            }
+            if (t.y == 0) {  // one event with more entries than a tile holds: this plan stays with the sweep kernels
+                plan->small.unsupported = true;
+                return MCDP_OK;
+            }
+            tiles.push_back(t);
+        }
+    }
+    int32_t rc = upload(plan->small.items, items);
+    if (!rc) rc = upload(plan->small.events, h.events);
+    if (!rc) rc = upload(plan->small.pred_src, src);
+    if (!rc) rc = upload(plan->small.pred_act, act);
+    if (!rc) rc = upload(plan->small.tiles, tiles);
+    if (rc) return rc;
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = plan->device;
+    MCDP_CUDA(cudaMemPoolCreate(&plan->small.pool, &props));
+    uint64_t keep = UINT64_MAX;  // freed scratch stays with the pool: a loop of run(seed) calls allocates once
+    MCDP_CUDA(cudaMemPoolSetAttribute(plan->small.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    MCDP_CUDA(cudaFuncSetAttribute(small_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSmallTilePreds * 12));
+    plan->small.n_items = int32_t(items.size());
+    plan->small.n_tiles = int32_t(tiles.size());
+    plan->small.ready = true;
+    return MCDP_OK;
+}
+
+// MODE kModeFull: sample every activity, then propagate; kModeInjected: propagate p.inj
+template <int MODE>
+int32_t launch_small(mcdp_plan* plan, const SweepParams& p, cudaStream_t stream) {
+    if (p.n <= 0) return MCDP_OK;
+    const HostPlan& h = plan->host;
+    SmallParams sp{};
+    sp.items = plan->small.items.p;
+    sp.n_items = plan->small.n_items;
+    sp.events = plan->small.events.p;
+    sp.pred_src = plan->small.pred_src.p;
+    sp.pred_act = plan->small.pred_act.p;
+    sp.tiles = plan->small.tiles.p;
+    sp.n_tiles = plan->small.n_tiles;
+    sp.P = h.P;
+    sp.dists = p.dists;
+    sp.tab_pool = p.tab_pool;
+    sp.log_tab = p.log_tab;
+    sp.seeds = p.seeds;
+    sp.seed0 = p.seed0;
+    sp.n = p.n;
+    sp.ld = p.ld;
+    sp.realized = p.realized;
+    sp.durations = p.durations;
+    sp.durations_in = p.inj;
+    sp.cause = p.cause;
+    sp.max_delay = p.max_delay;
+    sp.keys = p.keys;
+    void* scratch = nullptr;
+    MCDP_CUDA(cudaMallocFromPoolAsync(&scratch, size_t(std::max<int64_t>(h.P, 1)) * size_t(p.n) * 8, plan->small.pool, stream));
+    sp.dur_by_pred = static_cast<double*>(scratch);
+    cudaError_t e = cudaSuccess;
+    if (MODE == kModeFull) {
+        if (sp.n_items > 0) {
+            NvtxRange nvtx("mcdp:small sample");
+            const dim3 grid(unsigned((sp.n_items + kSmallSampleThreads - 1) / kSmallSampleThreads), unsigned(p.n));
+            small_sample_kernel<<<grid, kSmallSampleThreads, 0, stream>>>(sp);
+            e = cudaGetLastError();
+        }
+    } else if (h.P > 0) {
+        NvtxRange nvtx("mcdp:small gather");
+        const dim3 grid(unsigned((h.P + kSmallSampleThreads - 1) / kSmallSampleThreads), unsigned(p.n));
+        small_gather_kernel<<<grid, kSmallSampleThreads, 0, stream>>>(sp);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && h.E > 0) {
+        NvtxRange nvtx("mcdp:small propagate");
+        small_propagate_kernel<<<unsigned(p.n), kSmallSweepThreads, 2 * kSmallTilePreds * 12, stream>>>(sp);
+        e = cudaGetLastError();
+    }
+    const cudaError_t ef = cudaFreeAsync(scratch, stream);  // stream-ordered: after the kernels above
+    if (e == cudaSuccess) e = ef;
+    MCDP_CUDA(e);
+    return MCDP_OK;
+}
+
+// the sweep of one launch: the small-call path or the sweep kernels
+template <int MODE>
+int32_t launch_any(mcdp_plan* plan, const SweepParams& p, const LaunchShape& s, cudaStream_t stream) {
+    if (use_small(plan, p.n)) {
+        const int32_t rc = ensure_small(plan);
+        if (rc) return rc;
+        if (!plan->small.unsupported) return launch_small<MODE>(plan, p, stream);
+    }
+    return launch_sweep<MODE>(plan, p, s, stream);
+}
+
 // reference-compatible stream: draw durations[A][ld] with the Xoshiro sampler; the caller then
 // sweeps them in duration-injection mode
 int32_t launch_compat_sampler(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n, double* d_durations,
@@ -718,6 +884,10 @@ int32_t mcdp_plan_set_option(mcdp_plan* plan, int32_t option, int64_t value) {
                 return fail(MCDP_ERR_ARG, "cluster size must be 0 (auto), 1, 2, 4 or 8");
             plan->cluster_size = int(value);
             break;
+        case MCDP_OPT_SMALL_CALL_MAX:
+            if (value < -1 || value > 65535) return fail(MCDP_ERR_ARG, "small-call limit must be -1 (auto), 0 (never) or at most 65535 samples");
+            plan->small_max = value;
+            break;
         case MCDP_OPT_HOST_CHUNK:
             if (value < 0) return fail(MCDP_ERR_ARG, "host chunk must be non-negative");
             plan->host_chunk = value;
@@ -785,6 +955,11 @@ int64_t mcdp_plan_reduced_chunk(mcdp_plan* plan, int64_t n, int32_t n_bins, int3
 int32_t mcdp_plan_launch_shape(const mcdp_plan* plan, int64_t n, int32_t reduced, int32_t n_bins, int64_t* out8) {
     if (!plan || !out8) return fail(MCDP_ERR_ARG, "null argument");
     if (n < 0) return fail(MCDP_ERR_ARG, "n must be non-negative");
+    if (!reduced && use_small(plan, n)) {  // one thread per activity, then per event: one sample per "lane"
+        const int64_t shape[8] = {1, 0, 0, kSmallSweepThreads, n, 0, 1, 0};
+        std::copy(shape, shape + 8, out8);
+        return MCDP_OK;
+    }
     const LaunchShape s = choose_shape(plan, n, reduced != 0, n_bins);
     out8[0] = s.spl;
     out8[1] = s.wpg;
@@ -821,9 +996,9 @@ int32_t mcdp_run_full_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t se
         rc = launch_compat_sampler(plan, d_seeds, seed0, n, d_durations, ld, static_cast<cudaStream_t>(stream));
         if (rc) return rc;
         p.inj = d_durations;
-        return launch_sweep<kModeInjected>(plan, p, s, static_cast<cudaStream_t>(stream));
+        return launch_any<kModeInjected>(plan, p, s, static_cast<cudaStream_t>(stream));
     }
-    return launch_sweep<kModeFull>(plan, p, s, static_cast<cudaStream_t>(stream));
+    return launch_any<kModeFull>(plan, p, s, static_cast<cudaStream_t>(stream));
 }
 
 int32_t mcdp_run_injected_device(mcdp_plan* plan, const double* d_durations, int64_t n, double* d_realized,
@@ -842,7 +1017,7 @@ int32_t mcdp_run_injected_device(mcdp_plan* plan, const double* d_durations, int
     p.realized = d_realized;
     p.inj = d_durations;
     p.cause = d_cause;
-    return launch_sweep<kModeInjected>(plan, p, s, static_cast<cudaStream_t>(stream));
+    return launch_any<kModeInjected>(plan, p, s, static_cast<cudaStream_t>(stream));
 }
 
 int32_t mcdp_run_reduced_device(mcdp_plan* plan, const int32_t* d_seeds, int32_t seed0, int64_t n,
@@ -1013,9 +1188,9 @@ int32_t mcdp_run_many_host(mcdp_plan* plan, const int32_t* seeds, int64_t n, dou
             rc = launch_compat_sampler(plan, sl.seeds.p, 0, m, sl.durations.p, chunk, sl.stream);
             if (rc) break;
             p.inj = sl.durations.p;
-            rc = launch_sweep<kModeInjected>(plan, p, s, sl.stream);
+            rc = launch_any<kModeInjected>(plan, p, s, sl.stream);
         } else {
-            rc = launch_sweep<kModeFull>(plan, p, s, sl.stream);
+            rc = launch_any<kModeFull>(plan, p, s, sl.stream);
         }
         if (rc) break;
         if (realized && E) {
@@ -1078,7 +1253,7 @@ int32_t mcdp_run_injected_host(mcdp_plan* plan, const double* durations, int64_t
         p.realized = sl.realized.p;
         p.inj = sl.durations.p;
         p.cause = sl.cause.p;
-        rc = launch_sweep<kModeInjected>(plan, p, s, sl.stream);
+        rc = launch_any<kModeInjected>(plan, p, s, sl.stream);
         if (rc) break;
         if (realized && E) {
             MCDP_CUDA_BRK(sl.t_realized.ensure(size_t(E) * size_t(chunk)));

@@ -273,6 +273,8 @@ def test_auto_rule_clusters_small_launches_only():
     small, full = plan.launch_shape(2048), plan.launch_shape(18944)
     assert small["samples_per_lane"] == 4 and small["cluster"] == 4 and small["grid"] == 16 * 4
     assert full["cluster"] == 1 and full["grid"] == 148
+    assert plan.launch_shape(1)["samples_per_lane"] == 1  # a call of one sample: the small-call path (test_gpu_small_calls.py)
+    plan.set_option(capi.OPT_SMALL_CALL_MAX, 0)
     one = plan.launch_shape(1)
     assert one["samples_per_lane"] == 4 and one["cluster"] == 8 and one["grid"] == 8
 
