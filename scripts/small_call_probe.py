@@ -13,6 +13,8 @@ sys.path.insert(0, ROOT)
 from bench import build_workload  # noqa: E402
 from mc_dagprop_b200 import capi  # noqa: E402
 
+if os.environ.get("MCDP_LIB"):  # scratch A/B builds (scripts/ab_variants.sh)
+    capi.LIB_PATH = os.path.abspath(os.environ["MCDP_LIB"])
 wl = sys.argv[1] if len(sys.argv) > 1 else "c3"
 dag, dists = build_workload(wl)
 plan = capi.Plan(dag, dists, device=0)
