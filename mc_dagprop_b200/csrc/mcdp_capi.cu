@@ -577,14 +577,14 @@ int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
 // ---- calls of a handful of samples (mcdp_small_sweep.cuh) ----
 // Measured (profiles/r02_small_calls.txt): one CTA per sample, so up to a sample per SM the time grows slowly with the
-// number of samples -- 100k-event DAG 0.86 ms for one sample, 1.5 ms for 64, against 4.4 ms of the quad kernel's
-// cluster launch for anything up to 128; 1M-event DAG 6.9 ms against 35 ms; 50k-event chain 53 against 86 ms.  The
+// number of samples -- 100k-event DAG 0.66 ms for one sample, 1.3 ms for 64, against 4.4 ms of the quad kernel's
+// cluster launch for anything up to 128; 1M-event DAG 5.8 ms against 35 ms; 50k-event chain 46 against 86 ms.  The
 // sweep kernels' throughput wins from 100-250 samples on, the rule stays well below that.
 constexpr int64_t kSmallAutoMax = 64;
 constexpr int64_t kSmallScratchMax = int64_t(1) << 30;  // bytes of [samples][precedence entries] durations per call
 bool use_small(const mcdp_plan* plan, int64_t n) {
     if (n <= 0 || n > 65535 || plan->small.unsupported || plan->host.max_fan_in > kSmallTilePreds) return false;
-    if (plan->host.P * n * 8 > kSmallScratchMax && plan->small_max < 0) return false;
+    if ((plan->host.P + plan->host.E) * n * 8 > kSmallScratchMax && plan->small_max < 0) return false;
     if (plan->small_max >= 0) return n <= plan->small_max;
     // an explicit kernel choice (samples per lane, cluster size, warps per group) is a request for the sweep kernels
     if (plan->samples_per_lane || plan->cluster_size || plan->warps_per_group || plan->groups_per_cta) return false;
@@ -649,7 +649,7 @@ int32_t ensure_small(mcdp_plan* plan) {
     MCDP_CUDA(cudaMemPoolCreate(&plan->small.pool, &props));
     uint64_t keep = UINT64_MAX;  // freed scratch stays with the pool: a loop of run(seed) calls allocates once
     MCDP_CUDA(cudaMemPoolSetAttribute(plan->small.pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    MCDP_CUDA(cudaFuncSetAttribute(small_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kSmallTilePreds * 12));
+    MCDP_CUDA(cudaFuncSetAttribute(small_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmallStages * kSmallTilePreds * 12));
     plan->small.n_items = int32_t(items.size());
     plan->small.n_tiles = int32_t(tiles.size());
     plan->small.ready = true;
@@ -684,8 +684,10 @@ int32_t launch_small(mcdp_plan* plan, const SweepParams& p, cudaStream_t stream)
     sp.max_delay = p.max_delay;
     sp.keys = p.keys;
     void* scratch = nullptr;
-    MCDP_CUDA(cudaMallocFromPoolAsync(&scratch, size_t(std::max<int64_t>(h.P, 1)) * size_t(p.n) * 8, plan->small.pool, stream));
+    MCDP_CUDA(cudaMallocFromPoolAsync(&scratch, size_t(std::max<int64_t>(h.P + h.E, 1)) * size_t(p.n) * 8, plan->small.pool, stream));
     sp.dur_by_pred = static_cast<double*>(scratch);
+    sp.realized_by_sample = sp.dur_by_pred + h.P * p.n;
+    sp.E = h.E;
     cudaError_t e = cudaSuccess;
     if (MODE == kModeFull) {
         if (sp.n_items > 0) {
@@ -702,7 +704,7 @@ int32_t launch_small(mcdp_plan* plan, const SweepParams& p, cudaStream_t stream)
     }
     if (e == cudaSuccess && h.E > 0) {
         NvtxRange nvtx("mcdp:small propagate");
-        small_propagate_kernel<<<unsigned(p.n), kSmallSweepThreads, 2 * kSmallTilePreds * 12, stream>>>(sp);
+        small_propagate_kernel<<<unsigned(p.n), kSmallSweepThreads, kSmallStages * kSmallTilePreds * 12, stream>>>(sp);
         e = cudaGetLastError();
     }
     const cudaError_t ef = cudaFreeAsync(scratch, stream);  // stream-ordered: after the kernels above

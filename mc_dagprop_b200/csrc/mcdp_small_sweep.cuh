@@ -27,8 +27,7 @@ namespace mcdp {
 constexpr int kSmallSampleThreads = 256;
 constexpr int kSmallSweepThreads = 1024;
 constexpr int kSmallTileEvents = kSmallSweepThreads;
-constexpr int kSmallPrefetch = 4;  // precedence entries a thread fetches ahead per tile
-constexpr int kSmallTilePreds = kSmallPrefetch * kSmallSweepThreads;
+constexpr int kSmallTilePreds = 4 * kSmallSweepThreads;
 constexpr uint32_t kSmallNoPos = 0xFFFFFFFFu;
 #ifndef MCDP_SMALL_BATCH
 #define MCDP_SMALL_BATCH 4
@@ -45,6 +44,7 @@ struct SmallParams {
     const int4* tiles;         // {first event, events, first precedence entry, entries}
     int32_t n_tiles;
     int64_t P;
+    int32_t E;
     const DistRec* dists;
     const double* tab_pool;
     const double* log_tab;
@@ -55,6 +55,7 @@ struct SmallParams {
     double* durations;        // [A][ld] written by small_sample_kernel
     const double* durations_in;  // [A][ld] small_gather_kernel: the caller's injected durations
     double* dur_by_pred;      // [n][P] duration of every precedence entry: what the propagate kernel streams
+    double* realized_by_sample;  // [n][E] the sample's realized times side by side (the [E][ld] output has a row per event)
     int32_t* cause;           // [E][ld]
     double max_delay;
     PhiloxKeys keys;
@@ -95,75 +96,86 @@ __global__ void __launch_bounds__(kSmallSampleThreads) small_gather_kernel(const
 }
 
 // One CTA per sample, tile after tile, one thread per event of the tile.  What does not depend on earlier levels --
-// the event records, the sources and durations of the precedence entries -- is fetched one tile ahead (registers,
-// then shared memory); on the critical path of a level are the realized times of the sources (L2), the fold and a barrier.
+// the event records (registers), the sources and durations of the precedence entries (cp.async straight into a
+// ring of shared-memory tiles, no registers) -- is fetched two tiles ahead; on the critical path of a level are
+// the realized times of the sources (L2, kSmallBatch requests at a time), the fold and a barrier.
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {  // at most N of the thread's groups still pending
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kSmallStages = 3;  // shared-memory tiles: the one being folded and two in flight
+
 __global__ void __launch_bounds__(kSmallSweepThreads) small_propagate_kernel(const __grid_constant__ SmallParams p) {
     extern __shared__ __align__(16) unsigned char small_smem[];
-    // two buffers of {duration f64[kSmallTilePreds], source row u32[kSmallTilePreds]}
+    // kSmallStages buffers of {duration f64[kSmallTilePreds], source row u32[kSmallTilePreds]}
     constexpr int kBufBytes = kSmallTilePreds * 12;
+    const uint32_t smem0 = smem_u32(small_smem);
     const int64_t s = blockIdx.x;
     const int tid = int(threadIdx.x);
     const double* dur = p.dur_by_pred + s * p.P;
+    double* mine = p.realized_by_sample + s * int64_t(p.E);  // what later levels read: neighbours share sectors
 
     struct Ahead {
-        int4 tile;        // descriptor
-        int4 h0, h1;      // this thread's event record of the tile
-        uint32_t src[kSmallPrefetch];
-        double d[kSmallPrefetch];
+        int n_ev, pred0;      // of the tile
+        int4 h0;              // this thread's event record: row, event, pred_begin, fan_in
+        int e_lo, e_hi;       // earliest
     };
-    auto fetch = [&](int t, Ahead& a) {
-        a.tile = make_int4(0, 0, 0, 0);
-        if (t >= p.n_tiles) return;
-        a.tile = __ldg(p.tiles + t);
-        if (tid < a.tile.y) {
-            a.h0 = __ldg(reinterpret_cast<const int4*>(p.events + a.tile.x + tid));
-            a.h1 = __ldg(reinterpret_cast<const int4*>(p.events + a.tile.x + tid) + 1);
+    auto load_desc = [&](int t) { return t < p.n_tiles ? __ldg(p.tiles + t) : make_int4(0, 0, 0, 0); };
+    // tile t (descriptor already in registers): event record into registers, entries by cp.async into buffer t % stages
+    auto fetch = [&](int t, const int4& tile, Ahead& a) {
+        a.n_ev = tile.y;
+        a.pred0 = tile.z;
+        if (tid < tile.y) {
+            a.h0 = __ldg(reinterpret_cast<const int4*>(p.events + tile.x + tid));
+            const int2 e = __ldg(reinterpret_cast<const int2*>(p.events + tile.x + tid) + 2);
+            a.e_lo = e.x;
+            a.e_hi = e.y;
         }
-#pragma unroll
-        for (int r = 0; r < kSmallPrefetch; ++r) {
-            const int j = tid + r * kSmallSweepThreads;
-            if (j < a.tile.w) {
-                a.src[r] = __ldg(p.pred_src + uint32_t(a.tile.z) + j);
-                a.d[r] = __ldcs(dur + uint32_t(a.tile.z) + j);
-            }
+        const uint32_t d_s = smem0 + uint32_t((t % kSmallStages) * kBufBytes), src_s = d_s + uint32_t(kSmallTilePreds * 8);
+        for (int j = tid; j < tile.w; j += kSmallSweepThreads) {
+            cp_async_8(d_s + uint32_t(j) * 8u, dur + uint32_t(tile.z) + j);
+            cp_async_4(src_s + uint32_t(j) * 4u, p.pred_src + uint32_t(tile.z) + j);
         }
-    };
-    auto park = [&](const Ahead& a, int buf) {  // the fetched entries into the tile's shared-memory buffer
-        double* d_s = reinterpret_cast<double*>(small_smem + buf * kBufBytes);
-        uint32_t* src_s = reinterpret_cast<uint32_t*>(small_smem + buf * kBufBytes + kSmallTilePreds * 8);
-#pragma unroll
-        for (int r = 0; r < kSmallPrefetch; ++r) {
-            const int j = tid + r * kSmallSweepThreads;
-            if (j < a.tile.w) {
-                d_s[j] = a.d[r];
-                src_s[j] = a.src[r];
-            }
-        }
+        cp_async_commit();
     };
 
-    Ahead cur, nxt;
-    fetch(0, cur);
-    park(cur, 0);
+    // Software pipeline: while tile t is folded, the entries of tiles t + 1 and t + 2 are in flight and the descriptor
+    // of tile t + 3 is on its way -- no load of the static data is waited for in the iteration that issued it.
+    Ahead cur, nx1, nx2;
+    fetch(0, load_desc(0), cur);
+    fetch(1, load_desc(1), nx1);
+    int4 desc2 = load_desc(2);
+    cp_async_wait_group<1>();
     __syncthreads();
     for (int t = 0; t < p.n_tiles; ++t) {
-        fetch(t + 1, nxt);  // in flight while this tile is folded
-        const int buf = t & 1;
-        if (tid < cur.tile.y) {
+        const int4 desc3 = load_desc(t + 3);
+        fetch(t + 2, desc2, nx2);
+        desc2 = desc3;
+        const int buf = t % kSmallStages;
+        if (tid < cur.n_ev) {
             const double* d_s = reinterpret_cast<const double*>(small_smem + buf * kBufBytes);
             const uint32_t* src_s = reinterpret_cast<const uint32_t*>(small_smem + buf * kBufBytes + kSmallTilePreds * 8);
             // _core.cpp:333-337
-            const double earliest = __hiloint2double(cur.h1.y, cur.h1.x);
+            const double earliest = __hiloint2double(cur.e_hi, cur.e_lo);
             const double ub = __dadd_rn(earliest, p.max_delay);
             double lat = earliest;
             int cause = -1;
-            const int rel = cur.h0.z - cur.tile.z, fan = cur.h0.w;
+            const int rel = cur.h0.z - cur.pred0, fan = cur.h0.w;
             for (int k0 = 0; k0 < fan; k0 += kSmallBatch) {
                 uint32_t src[kSmallBatch];
                 double rs[kSmallBatch];
 #pragma unroll
                 for (int k = 0; k < kSmallBatch; ++k) {  // the realized times of several sources at once
                     src[k] = k0 + k < fan ? src_s[rel + k0 + k] : 0u;
-                    if (k0 + k < fan) rs[k] = __ldcg(p.realized + int64_t(src[k]) * p.ld + s);
+                    if (k0 + k < fan) rs[k] = __ldcg(mine + src[k]);
                 }
 #pragma unroll
                 for (int k = 0; k < kSmallBatch; ++k) {
@@ -178,12 +190,15 @@ __global__ void __launch_bounds__(kSmallSweepThreads) small_propagate_kernel(con
                 }
             }
             // _core.cpp:348-349
-            __stcg(p.realized + int64_t(uint32_t(cur.h0.x)) * p.ld + s, ref_min(lat, ub));
-            __stcg(p.cause + int64_t(uint32_t(cur.h0.x)) * p.ld + s, cause);
+            const double r = ref_min(lat, ub);
+            __stcg(mine + uint32_t(cur.h0.x), r);
+            __stcs(p.realized + int64_t(uint32_t(cur.h0.x)) * p.ld + s, r);
+            __stcs(p.cause + int64_t(uint32_t(cur.h0.x)) * p.ld + s, cause);
         }
-        park(nxt, buf ^ 1);
-        cur = nxt;
-        __syncthreads();  // the tile's realized times are in L2, the next tile's entries in shared memory
+        cur = nx1;
+        nx1 = nx2;
+        cp_async_wait_group<1>();  // tile t + 1 has landed (tile t + 2 may still be in flight)
+        __syncthreads();           // the tile's realized times are in L2, the next tile's entries in shared memory
     }
 }
 
