@@ -38,9 +38,10 @@ if reduced:
             torch.zeros((3, E), dtype=torch.int64, device=dev), torch.zeros((E, 64), dtype=torch.int32, device=dev)]
     step = lambda i: plan.run_reduced_device(n, desc, *bufs, seed0=i * n, stream=st)
 else:
-    r = torch.empty((E, n), dtype=torch.float64, device=dev); du = torch.empty((A, n), dtype=torch.float64, device=dev)
-    c = torch.empty((E, n), dtype=torch.int32, device=dev)
-    step = lambda i: plan.run_full_device(n, r, du, c, n, seed0=i * n, stream=st)
+    ld = (n + 63) // 64 * 64  # row length of the event-major arrays: a multiple of 64
+    r = torch.empty((E, ld), dtype=torch.float64, device=dev); du = torch.empty((A, ld), dtype=torch.float64, device=dev)
+    c = torch.empty((E, ld), dtype=torch.int32, device=dev)
+    step = lambda i: plan.run_full_device(n, r, du, c, ld, seed0=i * n, stream=st)
 ts = []
 for i in range(a.reps + 1):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
