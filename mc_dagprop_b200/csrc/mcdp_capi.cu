@@ -581,6 +581,7 @@ int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 // cluster launch for anything up to 128; 1M-event DAG 5.8 ms against 35 ms; 50k-event chain 46 against 86 ms.  The
 // sweep kernels' throughput wins from 100-250 samples on, the rule stays well below that.
 constexpr int64_t kSmallAutoMax = 64;
+constexpr int64_t kSmallMidPreds = int64_t(1) << 20;  // precedence entries up to which 128 samples still take that path
 constexpr int64_t kSmallScratchMax = int64_t(1) << 30;  // bytes of [samples][precedence entries] durations per call
 bool use_small(const mcdp_plan* plan, int64_t n) {
     if (n <= 0 || n > 65535 || plan->small.unsupported || plan->host.max_fan_in > kSmallTilePreds) return false;
@@ -588,7 +589,9 @@ bool use_small(const mcdp_plan* plan, int64_t n) {
     if (plan->small_max >= 0) return n <= plan->small_max;
     // an explicit kernel choice (samples per lane, cluster size, warps per group) is a request for the sweep kernels
     if (plan->samples_per_lane || plan->cluster_size || plan->warps_per_group || plan->groups_per_cta) return false;
-    return n <= std::min<int64_t>(kSmallAutoMax, plan->sm_count);
+    // up to 64 samples on any DAG; up to 128 (still one CTA per SM) where a sample's pass is short
+    const int64_t limit = plan->host.P <= kSmallMidPreds ? 2 * kSmallAutoMax : kSmallAutoMax;
+    return n <= std::min<int64_t>(limit, plan->sm_count);
 }
 
 int32_t ensure_small(mcdp_plan* plan) {
